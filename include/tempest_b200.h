@@ -1,0 +1,238 @@
+/*
+ * tempest_b200.h -- C ABI of libtempest_b200.so (sm_100a kernels for the Persistent
+ * Sampling inner loop of minaskar/tempest).
+ *
+ * Contract: every entry point takes raw DEVICE pointers + sizes + a
+ * cudaStream_t (passed as void*), enqueues work on that stream and returns immediately
+ * with 0 or a TB_ERR_* / cudaError code.  No entry point allocates or frees caller-visible
+ * memory, synchronises the device, or throws.  Scratch memory is supplied by the caller
+ * (sizes come from the *_workspace_bytes queries).  All floating point is IEEE fp64;
+ * indices are int64.  "ref:" cites the reference function (relative to /root/reference)
+ * each entry point replaces; INTEGRATION.md shows the binding a maintainer would add.
+ */
+#ifndef TEMPEST_B200_H
+#define TEMPEST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tb_stream_t; /* cudaStream_t */
+
+enum {
+  TB_OK = 0,
+  TB_ERR_ARG = -1,       /* bad argument (null pointer, negative size, unsupported n_dim ...) */
+  TB_ERR_WORKSPACE = -2, /* workspace too small */
+  TB_ERR_UNSUPPORTED = -3
+};
+
+/* likelihood / prior kernel ids (tempest_b200/registry.py) */
+enum { TB_LIKE_ROSENBROCK = 0, TB_LIKE_GAUSSIAN = 1, TB_LIKE_ISO_MIXTURE = 2, TB_LIKE_TWIN_SHELLS = 3 };
+enum { TB_PRIOR_AFFINE = 0 };
+enum { TB_SAMPLE_TPCN = 0, TB_SAMPLE_RWM = 1 };
+enum { TB_RNG_PHILOX = 0, TB_RNG_TAPE = 1 };
+
+int tb_version(void);
+int tb_sm_count(void); /* SM count of the current device (grids are sized from it) */
+
+/* ------------------------------------------------------------------------------------
+ * (a) persistent-ensemble reweighting.   ref: tempest/state_manager.py:418-480
+ *
+ * C_s = LSE_t( l_s*beta_t - logZ_t + log n_t )  (sequential logaddexp in generation order).
+ * The reference rebuilds the N_total x T matrix for every probe; C_s does not depend on the
+ * probe beta, so it is cached and updated incrementally (bitwise equal to a full rebuild).
+ * gen_beta/gen_logz/gen_logn are DEVICE arrays of length T.
+ * ---------------------------------------------------------------------------------- */
+int tb_mixture_build(const double* logl, double* C, int64_t n_total,
+                     const double* gen_beta, const double* gen_logz, const double* gen_logn,
+                     int32_t T, tb_stream_t stream);
+/* particles [0,n_old) get the one new term (generation T_new-1) folded in; particles
+ * [n_old, n_old+n_new) get the full T_new-term sum. */
+int tb_mixture_append(const double* logl, double* C, int64_t n_old, int64_t n_new,
+                      const double* gen_beta, const double* gen_logz, const double* gen_logn,
+                      int32_t T_new, tb_stream_t stream);
+
+/* (b) one ESS probe.   ref: steps/reweight.py:88-118 + tools.py:120-135
+ * a_s = beta*l_s - C_s ; out = {m = max a, S1 = sum exp(a-m), S2 = sum exp(a-m)^2,
+ * ESS = S1^2/S2, logZ = m + log S1, n_nonfinite}.  workspace: tb_probe_workspace_bytes(). */
+size_t tb_probe_workspace_bytes(void);
+int tb_probe(const double* logl, const double* C, int64_t n_total, double beta,
+             void* workspace, double* out6, tb_stream_t stream);
+
+/* normalised importance weights at beta: w_s = exp(a_s - m) / S1 with (m,S1) read from the
+ * device-resident probe result `stats` (out6 of tb_probe at the same beta).
+ * ref: steps/reweight.py:299-339 (w / sum w), state_manager.py:473 */
+int tb_weights(const double* logl, const double* C, int64_t n_total, double beta,
+               const double* stats, double* w, tb_stream_t stream);
+/* normalised log-weights logw_s = a_s - (m + log S1)  (posterior(return_logw=True),
+ * core.py:197,233-242) */
+int tb_log_weights(const double* logl, const double* C, int64_t n_total, double beta,
+                   const double* stats, double* logw, tb_stream_t stream);
+
+/* (b) device-side next-beta search: ESS bracket + bisection with the reference's branch
+ * logic and constants (steps/reweight.py:123-297, config.py:233-237) in ONE cooperative
+ * launch -- no host round trip per probe.
+ *   flags bit0: skip the "ESS(beta_prev) <= target -> stay" probe (host already decided it).
+ *   result16[0]=beta, [1]=m, [2]=S1, [3]=S2, [4]=ESS, [5]=logZ(beta), [6]=n_probes,
+ *   [7]=beta_low==beta_high flag, [8]=non-finite count; probe_log (may be NULL) receives
+ *   (beta,ESS) pairs, at most probe_log_cap pairs.  logl and C must be 16-byte aligned. */
+size_t tb_next_beta_workspace_bytes(void);
+int tb_next_beta(const double* logl, const double* C, int64_t n_total, double beta_prev,
+                 double ess_target, int32_t flags, void* workspace, double* result16,
+                 double* probe_log, int32_t probe_log_cap, tb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (c) resampling.   ref: steps/resample.py:52-99, tools.py:178-228, numpy legacy choice
+ *
+ * tb_cdf_exact reproduces numpy's strictly sequential fp64 cumsum BIT FOR BIT with a
+ * parallel algorithm (binade-segmented integer scan); tb_cdf_sequential is the
+ * one-thread literal form kept for cross-checks.  p must be non-negative.
+ * ---------------------------------------------------------------------------------- */
+size_t tb_cdf_workspace_bytes(int64_t n);
+int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_stream_t stream);
+int tb_cdf_sequential(const double* p, int64_t n, double* cdf, tb_stream_t stream);
+/* multinomial: idx_k = #{ j : cdf_j / cdf_{n-1} <= U_k }   (searchsorted side='right') */
+int tb_search_right(const double* cdf, int64_t n, const double* draws, int64_t m,
+                    int64_t* idx, tb_stream_t stream);
+/* systematic: pos_k = (u0 + k)/m ; idx_k = first j with cdf_j >= pos_k ; *overflow is set
+ * to 1 if some pos_k exceeds cdf_{n-1} (the reference raises IndexError there). */
+int tb_systematic(const double* cdf, int64_t n, double u0, int64_t m, int64_t* idx,
+                  int32_t* overflow, tb_stream_t stream);
+/* gather rows of the persistent ensemble into the active set (row-major [m,d]) */
+int tb_gather_rows(const double* hist_u, const double* hist_logl, int32_t d,
+                   const int64_t* idx, int64_t m, double* act_u, double* act_logl,
+                   tb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (e) moments / volume variation / trim / Student-t mode statistics
+ * ---------------------------------------------------------------------------------- */
+/* mean_j = sum_s w_s u_sj ; cov = sum_s w_s (u_s-mean)(u_s-mean)^T  (w normalised).
+ * ref: tools.py:94-99.  workspace: tb_moments_workspace_bytes(d). */
+size_t tb_moments_workspace_bytes(int32_t d);
+int tb_weighted_moments(const double* u, const double* w, int64_t n, int32_t d,
+                        void* workspace, double* mean, double* cov, tb_stream_t stream);
+/* cv = 0.5*sqrt( sum_s w_s^2 clip(d2_s - d, +-1e6)^2 ), d2_s = (u_s-mean)^T cov_inv (u_s-mean).
+ * ref: tools.py:111-115 */
+int tb_mahalanobis_cv(const double* u, const double* w, int64_t n, int32_t d,
+                      const double* mean, const double* cov_inv, void* workspace,
+                      double* cv_out, tb_stream_t stream);
+/* batched d x d Cholesky + inverse with the reference's regularise-on-failure rule
+ * (modes.py:105-119): on a non-positive pivot add max(1e-6, 1e-6*|tr|) to the diagonal (the
+ * regularised matrix is written back to `a`) and retry.  info[k] = 0 ok, 1 regularised,
+ * 2 failed even after regularisation.  norms3[k] = {|A|_F, |A^-1|_F, tr A}: |A|_F*|A^-1|_F
+ * bounds cond_2 from above and screens the rank test of tools.py:101. */
+int tb_chol_inv(double* a, int32_t d, int32_t batch, double* chol, double* inv,
+                int32_t* info, double* norms3, tb_stream_t stream);
+/* Sigma = cov_ddof1*(M-1)/M + diag(var_ddof0)/M from the count-weighted scatter matrix
+ * (student.py:63) */
+int tb_student_sigma(const double* scatter, int32_t d, double m_total, double* sigma,
+                     tb_stream_t stream);
+/* med[c] = (pair[2c] + pair[2c+1]) / 2  (np.median of an even count, student.py:62) */
+int tb_median_pairs(const double* pair, int32_t d, double* med, tb_stream_t stream);
+/* cov += factor * trace(cov) * I   (tools.py:101-104 regularisation, factor = 1e-6) */
+int tb_add_trace_reg(double* cov, int32_t d, double factor, tb_stream_t stream);
+
+/* trim_weights (tools.py:10-55).  Step kernels; the <=1000-threshold scan is driven by the
+ * host step object (tempest_b200/steps.py) as a binary search over the monotone criterion.
+ *   tb_normalize_inplace : w /= sum(w) ; stats3 = {sum before, sum w^2 after, max after}
+ *   tb_binade_hist       : per-binade (exponent) count / sum w / sum w^2, 2048 bins
+ *   tb_select_ranks      : exact order statistics by 6 MSD radix passes of 11 bits
+ *   tb_masked_sums       : {count, sum w, sum w^2} over w >= thr
+ *   tb_compact_ge        : ordered stream compaction of {s : w_s >= thr} -> idx, w/denom
+ */
+size_t tb_reduce_workspace_bytes(void);
+int tb_normalize_inplace(double* w, int64_t n, void* workspace, double* stats3, tb_stream_t stream);
+int tb_binade_hist(const double* w, int64_t n, uint64_t* count2048, double* s1_2048,
+                   double* s2_2048, tb_stream_t stream);
+int tb_masked_sums(const double* w, int64_t n, double thr, void* workspace, double* out3,
+                   tb_stream_t stream);
+size_t tb_compact_workspace_bytes(int64_t n);
+int tb_compact_ge(const double* w, int64_t n, double thr, double denom, void* workspace,
+                  int64_t* idx_out, double* w_out, int64_t* n_out, tb_stream_t stream);
+
+/* exact k-th order statistics (0-based ranks, ascending) of non-negative doubles with
+ * integer multiplicities.  keys are read as  base[ (rows ? rows[j] : j) * stride + col ],
+ * j < n, col < ncols; mult may be NULL (all ones).  For each column the `nranks` ranks
+ * (ascending) are resolved simultaneously.  workspace: tb_select_workspace_bytes(ncols,nranks).
+ * Used for np.percentile order statistics (tools.py:46) and np.median (student.py:62). */
+size_t tb_select_workspace_bytes(int32_t ncols, int32_t nranks);
+int tb_select_ranks(const double* base, const int64_t* rows, int64_t stride, int64_t n,
+                    int32_t ncols, const int32_t* mult, const int64_t* ranks, int32_t nranks,
+                    void* workspace, double* out /*[ncols*nranks]*/, tb_stream_t stream);
+
+/* multiplicity of each trimmed row among the 4n training draws: counts[idx[k]] += 1 */
+int tb_count_indices(const int64_t* idx, int64_t m, int32_t* counts, int64_t n, tb_stream_t stream);
+/* count-weighted mean and scatter of u[rows[j]] (multiplicity mult[j]):
+ *   mean = sum c_j u_j / M ; scatter = sum c_j (u_j-mean)(u_j-mean)^T ; M = sum c_j
+ * ref: student.py:63 (np.cov / np.var of the 4n-row resampled set, modes.py:272-275) */
+int tb_counted_moments(const double* u, const int64_t* rows, const int32_t* mult, int64_t n,
+                       int32_t d, double inv_total, void* workspace, double* mean,
+                       double* scatter, tb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * (d) mutation.   ref: steps/mutate.py:76-200, mcmc.py:104-323
+ * ---------------------------------------------------------------------------------- */
+typedef struct tb_tape {
+  /* TB_RNG_TAPE: variates recorded from the oracle's stream */
+  const double* gamma;    /* [steps][n]  standard-gamma variates (tpCN) */
+  const double* acc_u;    /* [steps][n]  accept uniforms */
+  const double* z;        /* flat normals; attempt a of walker k at step t starts at z_off[t*n+k] + a*d */
+  const int64_t* z_off;   /* [steps][n] */
+  const int32_t* z_cnt;   /* [steps][n] attempts recorded */
+  int32_t steps;          /* steps available on the tape */
+} tb_tape;
+
+typedef struct tb_mcmc_params {
+  int32_t n_dim, n_modes, sampler, rng_mode;
+  int32_t like_id, prior_id;
+  int32_t n_steps, n_max;          /* per-dimension base / max step counts (config.py:80-84) */
+  double beta;
+  uint64_t seed, iteration;         /* Philox key material */
+  int64_t slot_offset;              /* global slot id of local walker 0 (multi-GPU) */
+  int64_t n_global;                 /* global walker count (== n when not sharded) */
+  const double* like_params;        /* device */
+  const double* prior_params;       /* device */
+  const double* mode_mean;          /* [K][d] device */
+  const double* mode_chol;          /* [K][d][d] lower, row-major */
+  const double* mode_inv;           /* [K][d][d] */
+  const double* mode_dof;           /* [K] */
+  const uint8_t* bc_kind;           /* [d] 0 strict, 1 periodic, 2 reflective; NULL = all strict */
+} tb_mcmc_params;
+
+/* warm-up draw at beta = 0: u = uniforms (tape `prior_u` [n][d] or Philox), x = prior(u),
+ * logl = L(x).  ref: steps/mutate.py:100-120 */
+int tb_prior_draw(int64_t n, const tb_mcmc_params* p, const double* prior_u_tape,
+                  double* u, double* x, double* logl, tb_stream_t stream);
+/* x = prior(u), optionally logl = L(x), for rows of u (posterior() / history export) */
+int tb_transform(const double* u, int64_t n, const tb_mcmc_params* p, double* x, double* logl,
+                 tb_stream_t stream);
+
+/* control block layout (doubles), device resident, written by the step kernel:
+ *  [0] steps done  [1] done flag  [2] sum accept (last step)  [3] mean alpha (last step)
+ *  [4] error flag (1 = tape exhausted, 2 = non-finite)  [5] total proposals drawn
+ *  [8 .. 8+K)       sigma_c
+ *  [8+K .. 8+2K)    walkers per mode (filled by tb_mcmc_begin)
+ *  [8+2K .. 8+3K)   sum alpha per mode of the last step */
+size_t tb_mcmc_workspace_bytes(int64_t n, int32_t n_modes);
+size_t tb_mcmc_ctrl_doubles(int32_t n_modes);
+/* reset the control block (sigma_c init, mcmc.py:222-223/298-299), count walkers per mode and
+ * cache q_k = (u_k-mu)^T Sigma^-1 (u_k-mu) of the starting state (tpCN) */
+int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, const double* u,
+                  double* qcur, void* workspace, double* ctrl, tb_stream_t stream);
+/* enqueue `count` Metropolis steps (each exits immediately once the stop rule has fired) */
+int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign,
+                  double* u, double* logl, double* qcur, void* workspace, double* ctrl,
+                  int32_t count, tb_stream_t stream);
+
+/* out[i] = uniform [0,1) number i+offset of stream (seed, iteration, purpose): the draws the
+ * host-driven resampling / training steps consume in Philox mode (purpose 4 / 5) */
+int tb_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t purpose, int64_t offset,
+                      int64_t n, double* out, tb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEMPEST_B200_H */

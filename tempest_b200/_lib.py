@@ -1,0 +1,115 @@
+"""ctypes binding of libtempest_b200.so (the C ABI declared in include/tempest_b200.h).
+
+The library is the product: there is no CPU or torch fallback.  ``load()`` raises
+``RuntimeError`` when the shared object is missing or CUDA is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtempest_b200.so")
+
+c_i32, c_i64, c_u32, c_u64, c_f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
+PTR = C.c_void_p
+SIZE = C.c_size_t
+
+
+class TbTape(C.Structure):
+    _fields_ = [("gamma", PTR), ("acc_u", PTR), ("z", PTR), ("z_off", PTR), ("z_cnt", PTR),
+                ("steps", c_i32)]
+
+
+class TbMcmcParams(C.Structure):
+    _fields_ = [
+        ("n_dim", c_i32), ("n_modes", c_i32), ("sampler", c_i32), ("rng_mode", c_i32),
+        ("like_id", c_i32), ("prior_id", c_i32), ("n_steps", c_i32), ("n_max", c_i32),
+        ("beta", c_f64), ("seed", c_u64), ("iteration", c_u64), ("slot_offset", c_i64),
+        ("n_global", c_i64), ("like_params", PTR), ("prior_params", PTR), ("mode_mean", PTR),
+        ("mode_chol", PTR), ("mode_inv", PTR), ("mode_dof", PTR), ("bc_kind", PTR),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/tempest_b200.h
+SIGNATURES = {
+    "tb_version": (c_i32, []),
+    "tb_sm_count": (c_i32, []),
+    "tb_mixture_build": (c_i32, [PTR, PTR, c_i64, PTR, PTR, PTR, c_i32, PTR]),
+    "tb_mixture_append": (c_i32, [PTR, PTR, c_i64, c_i64, PTR, PTR, PTR, c_i32, PTR]),
+    "tb_probe_workspace_bytes": (SIZE, []),
+    "tb_probe": (c_i32, [PTR, PTR, c_i64, c_f64, PTR, PTR, PTR]),
+    "tb_weights": (c_i32, [PTR, PTR, c_i64, c_f64, PTR, PTR, PTR]),
+    "tb_log_weights": (c_i32, [PTR, PTR, c_i64, c_f64, PTR, PTR, PTR]),
+    "tb_next_beta_workspace_bytes": (SIZE, []),
+    "tb_next_beta": (c_i32, [PTR, PTR, c_i64, c_f64, c_f64, c_i32, PTR, PTR, PTR, c_i32, PTR]),
+    "tb_cdf_workspace_bytes": (SIZE, [c_i64]),
+    "tb_cdf_exact": (c_i32, [PTR, c_i64, PTR, PTR, PTR]),
+    "tb_cdf_sequential": (c_i32, [PTR, c_i64, PTR, PTR]),
+    "tb_search_right": (c_i32, [PTR, c_i64, PTR, c_i64, PTR, PTR]),
+    "tb_systematic": (c_i32, [PTR, c_i64, c_f64, c_i64, PTR, PTR, PTR]),
+    "tb_gather_rows": (c_i32, [PTR, PTR, c_i32, PTR, c_i64, PTR, PTR, PTR]),
+    "tb_moments_workspace_bytes": (SIZE, [c_i32]),
+    "tb_weighted_moments": (c_i32, [PTR, PTR, c_i64, c_i32, PTR, PTR, PTR, PTR]),
+    "tb_mahalanobis_cv": (c_i32, [PTR, PTR, c_i64, c_i32, PTR, PTR, PTR, PTR, PTR]),
+    "tb_chol_inv": (c_i32, [PTR, c_i32, c_i32, PTR, PTR, PTR, PTR, PTR]),
+    "tb_student_sigma": (c_i32, [PTR, c_i32, c_f64, PTR, PTR]),
+    "tb_median_pairs": (c_i32, [PTR, c_i32, PTR, PTR]),
+    "tb_add_trace_reg": (c_i32, [PTR, c_i32, c_f64, PTR]),
+    "tb_reduce_workspace_bytes": (SIZE, []),
+    "tb_normalize_inplace": (c_i32, [PTR, c_i64, PTR, PTR, PTR]),
+    "tb_binade_hist": (c_i32, [PTR, c_i64, PTR, PTR, PTR, PTR]),
+    "tb_masked_sums": (c_i32, [PTR, c_i64, c_f64, PTR, PTR, PTR]),
+    "tb_compact_workspace_bytes": (SIZE, [c_i64]),
+    "tb_compact_ge": (c_i32, [PTR, c_i64, c_f64, c_f64, PTR, PTR, PTR, PTR, PTR]),
+    "tb_select_workspace_bytes": (SIZE, [c_i32, c_i32]),
+    "tb_select_ranks": (c_i32, [PTR, PTR, c_i64, c_i64, c_i32, PTR, PTR, c_i32, PTR, PTR, PTR]),
+    "tb_count_indices": (c_i32, [PTR, c_i64, PTR, c_i64, PTR]),
+    "tb_counted_moments": (c_i32, [PTR, PTR, PTR, c_i64, c_i32, c_f64, PTR, PTR, PTR, PTR]),
+    "tb_prior_draw": (c_i32, [c_i64, C.POINTER(TbMcmcParams), PTR, PTR, PTR, PTR, PTR]),
+    "tb_transform": (c_i32, [PTR, c_i64, C.POINTER(TbMcmcParams), PTR, PTR, PTR]),
+    "tb_mcmc_workspace_bytes": (SIZE, [c_i64, c_i32]),
+    "tb_mcmc_ctrl_doubles": (SIZE, [c_i32]),
+    "tb_mcmc_begin": (c_i32, [c_i64, C.POINTER(TbMcmcParams), PTR, PTR, PTR, PTR, PTR, PTR]),
+    "tb_mcmc_steps": (c_i32, [c_i64, C.POINTER(TbMcmcParams), C.POINTER(TbTape), PTR, PTR, PTR, PTR,
+                              PTR, PTR, c_i32, PTR]),
+    "tb_philox_uniform": (c_i32, [c_u64, c_u64, c_u32, c_i64, c_i64, PTR, PTR]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class TbError(RuntimeError):
+    pass
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """dlopen the library and attach signatures (no CUDA call is made)."""
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -m tempest_b200.build` "
+            "(there is no CPU fallback for the Persistent Sampling kernels)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def load() -> C.CDLL:
+    """Library handle for compute calls: requires a CUDA device."""
+    global _lib
+    if _lib is None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("tempest_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+        _lib = load_library()
+    return _lib
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        raise TbError(f"libtempest_b200: {what} failed with code {code}")

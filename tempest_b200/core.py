@@ -1,0 +1,214 @@
+"""Orchestrator of the device Persistent Sampling loop (reference: tempest/core.py).
+
+``execute_iteration`` = reweight -> train -> resample -> mutate -> commit (core.py:162-185);
+``run_sampling`` = the ``while _not_termination()`` loop (core.py:110-160, 360-374);
+``compute_posterior`` / ``compute_evidence`` (core.py:187-247).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import SamplerConfig
+from .ensemble import DeviceState, PersistentEnsemble, ptr, stream_ptr
+from .registry import is_registry_likelihood, is_registry_prior
+from .rng import PhiloxSource
+from .steps import F64, Kernels, ModeStats, Mutator, Resampler, Reweighter, Trainer
+
+
+class SamplerCore:
+    def __init__(self, config: SamplerConfig):
+        self.config = config
+        self._check_supported(config)
+        if not torch.cuda.is_available():
+            raise RuntimeError("tempest_b200 needs a CUDA device (sm_100a): there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = _lib.load()
+        self.k = Kernels(self.device)
+        self.ensemble = PersistentEnsemble(config.n_dim, self.device)
+        self.state = DeviceState(config.n_dim, core=self)
+        self.rng = PhiloxSource(config.random_state, self.device)
+        self.n_global = config.n_particles
+        self.slot_offset = 0
+        self.trace: dict = {}
+        self.n_mcmc_launches = 0
+        self.n_total = 0
+        self.logz_err = None
+        self._weights = None
+        like = config.log_likelihood.f if hasattr(config.log_likelihood, "f") else config.log_likelihood
+        self._like = like
+        self._like_params = torch.as_tensor(like.dparams(), dtype=F64).to(self.device)
+        self._prior_params = torch.as_tensor(config.prior_transform.dparams(), dtype=F64).to(self.device)
+        kinds = np.zeros(config.n_dim, dtype=np.uint8)
+        for j in (config.periodic or []):
+            kinds[j] = 1
+        for j in (config.reflective or []):
+            kinds[j] = 2
+        self._bc = torch.as_tensor(kinds).to(self.device) if kinds.any() else None
+        self.reweighter = Reweighter(self)
+        self.trainer = Trainer(self)
+        self.resampler = Resampler(self)
+        self.mutator = Mutator(self)
+
+    # -- what the CUDA path supports ----------------------------------------------------------
+    @staticmethod
+    def _check_supported(cfg: SamplerConfig) -> None:
+        if not cfg.vectorize:
+            raise NotImplementedError(
+                "tempest_b200 implements the vectorize=True path only (no per-sample pool.map, core.py:323-326)")
+        like = cfg.log_likelihood.f if hasattr(cfg.log_likelihood, "f") else cfg.log_likelihood
+        if not is_registry_likelihood(like) or not is_registry_prior(cfg.prior_transform):
+            raise NotImplementedError(
+                "the fused CUDA path evaluates registry priors/likelihoods in-kernel "
+                "(tempest_b200.registry: UniformPrior, Rosenbrock, GaussianLikelihood, IsotropicMixture, "
+                "TwinShells); arbitrary Python callables are a later row (SURVEY 8f-3)")
+        if cfg.clustering:
+            raise NotImplementedError(
+                "clustering=True (hierarchical Gaussian mixture, cluster.py) is not built yet (SURVEY 8f-2); "
+                "pass clustering=False")
+        if cfg.pool is not None:
+            raise NotImplementedError("pool is meaningless on the vectorised CUDA path")
+        if like.n_dim != cfg.n_dim or cfg.prior_transform.n_dim != cfg.n_dim:
+            raise ValueError("registry prior / likelihood dimension does not match n_dim")
+
+    # -- helpers used by the steps ---------------------------------------------------------------
+    @property
+    def warmup_regime(self) -> bool:
+        return self.ensemble.all_warmup()
+
+    def weights_buffer(self) -> torch.Tensor:
+        n = self.ensemble.n_total
+        if self._weights is None or self._weights.numel() < n:
+            self._weights = torch.empty(max(int(n * 1.5), 1024), dtype=F64, device=self.device)
+        return self._weights[:n]
+
+    def mcmc_params(self, beta: float, mode_stats: Optional[ModeStats]) -> _lib.TbMcmcParams:
+        cfg = self.config
+        p = _lib.TbMcmcParams()
+        p.n_dim = cfg.n_dim
+        p.n_modes = mode_stats.K if mode_stats is not None else 1
+        p.sampler = 1 if cfg.sample == "rwm" else 0
+        p.rng_mode = self.rng.mode
+        p.like_id = self._like.kernel_id
+        p.prior_id = cfg.prior_transform.kernel_id
+        p.n_steps = cfg.n_steps
+        p.n_max = cfg.n_max_steps
+        p.beta = float(beta)
+        p.seed = self.rng.seed
+        p.iteration = int(self.rng.iteration)
+        p.slot_offset = self.slot_offset
+        p.n_global = self.n_global
+        p.like_params = self._like_params.data_ptr()
+        p.prior_params = self._prior_params.data_ptr()
+        if mode_stats is not None:
+            p.mode_mean = mode_stats.means.data_ptr()
+            p.mode_chol = mode_stats.chol_covariances.data_ptr()
+            p.mode_inv = mode_stats.inv_covariances.data_ptr()
+            p.mode_dof = mode_stats.degrees_of_freedom.data_ptr()
+        p.bc_kind = self._bc.data_ptr() if self._bc is not None else None
+        return p
+
+    def transform_to_x(self, u: torch.Tensor) -> torch.Tensor:
+        """x = prior_transform(u) on the device (tb_transform)."""
+        n = int(u.shape[0])
+        x = torch.empty_like(u)
+        if n:
+            p = self.mcmc_params(0.0, None)
+            _lib.check(self.lib.tb_transform(ptr(u), n, C.byref(p), ptr(x), None, stream_ptr()), "tb_transform")
+        return x
+
+    def logw_and_logz(self, beta_final: float = 1.0, normalize: bool = True):
+        ens = self.ensemble
+        stats = self.k.probe(ens, beta_final, torch.zeros(16, dtype=F64, device=self.device))
+        out = torch.empty(ens.n_total, dtype=F64, device=self.device)
+        self.k.weights(ens, beta_final, stats, out, log=True)
+        h = stats.cpu().numpy()
+        logw = out.cpu().numpy()
+        if not normalize:
+            logw = logw + h[4] + np.log(ens.n_total)   # undo the normalisation: logw_s = a_s + log N
+        return logw, float(h[4])
+
+    # -- the PS loop ----------------------------------------------------------------------------
+    def _initialize_fresh(self) -> None:                 # core.py:376-381 (history is NOT cleared)
+        self.state.update_current({"iter": 0, "calls": 0, "beta": 0.0, "logz": 0.0})
+
+    def _not_termination(self) -> bool:                  # core.py:360-374
+        if self.ensemble.T == 0:
+            return True
+        h = self.k.probe(self.ensemble, 1.0).cpu().numpy()
+        self._last_posterior_probe = h
+        return 1.0 - float(self.state.raw("beta")) >= 1e-4 or h[3] < self.n_total
+
+    def execute_iteration(self, save_every=None, t0: int = 0) -> dict:
+        self.trace = {}
+        self.rng.begin_iteration(int(self.state.raw("iter") or 0) + 1)
+        weights = self.reweighter.run()
+        mode_stats = self.trainer.run(weights)
+        self.resampler.run(weights)
+        self.mutator.run(mode_stats)
+        # commit (state_manager.py:356-416): particles to the device ensemble, scalars to host lists
+        st = self.state
+        self.ensemble.append(st.raw("u"), st.raw("logl"), float(st.raw("beta")), float(st.raw("logz")))
+        st.commit_scalars()
+        self.last_mode_stats = mode_stats
+        return st.get_current()
+
+    def run_sampling(self, n_total: int = 4096, progress: bool = True, resume_state_path=None,
+                     save_every: Optional[int] = None) -> None:
+        if resume_state_path is not None or save_every is not None:
+            raise NotImplementedError("checkpoint/resume is outside the hot path (SURVEY 8f-4; upstream load is broken)")
+        self._initialize_fresh()
+        self.n_total = int(n_total)
+        pbar = None
+        if progress:
+            from tqdm import tqdm
+
+            pbar = tqdm(desc="Iter")
+        while self._not_termination():
+            self.execute_iteration()
+            if pbar is not None:
+                st = self.state
+                pbar.update(1)
+                pbar.set_postfix(beta=st.raw("beta"), calls=st.raw("calls"), ESS=int(st.raw("ess")),
+                                 logZ=st.raw("logz"), acc=st.raw("acceptance"), steps=st.raw("steps"))
+        self.state.set_current("logz", float(self._last_posterior_probe[4]))   # core.py:149-150
+        self.logz_err = None
+        if pbar is not None:
+            pbar.close()
+
+    # -- results ----------------------------------------------------------------------------------
+    def compute_posterior(self, resample=False, return_blobs=False, trim_importance_weights=True,
+                          return_logw=False, ess_trim=0.99, bins_trim=1000):
+        ens = self.ensemble
+        n = ens.n_total
+        k = self.k
+        stats = k.probe(ens, 1.0, torch.zeros(16, dtype=F64, device=self.device))
+        w = torch.empty(n, dtype=F64, device=self.device)
+        k.weights(ens, 1.0, stats, w)                     # core.py:197-199
+        logw = None
+        if return_logw:
+            lw = torch.empty(n, dtype=F64, device=self.device)
+            k.weights(ens, 1.0, stats, lw, log=True)
+            logw = lw.cpu().numpy()
+        u, logl = ens.u[:n], ens.logl[:n]
+        if trim_importance_weights:                        # core.py:210-220
+            idx, w = k.trim(w, n, ess=ess_trim, bins=bins_trim)
+            u, logl = u[idx], logl[idx]
+        if resample:                                       # core.py:222-231
+            m = int(w.numel())
+            cdf = k.cdf(w, m, "post_cdf")
+            idx = torch.empty(m, dtype=torch.int64, device=self.device)
+            k.systematic(cdf, m, self.rng.resample_u0(), m, idx)
+            u, logl = u[idx], logl[idx]
+            w = torch.full((m,), 1.0 / m, dtype=F64, device=self.device)
+        x = self.transform_to_x(u.contiguous())
+        out = (x.cpu().numpy(), w.cpu().numpy(), logl.cpu().numpy())
+        return out + (logw,) if return_logw else out
+
+    def compute_evidence(self):
+        return self.state.raw("logz"), self.logz_err

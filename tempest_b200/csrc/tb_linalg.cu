@@ -1,0 +1,161 @@
+// Small dense fp64 linear algebra on one CTA per matrix (d <= 128): Cholesky factor and inverse
+// of the mode covariances with the reference's regularise-on-failure rule.
+//   ref: tempest/modes.py:105-119 (ModeStatistics.__init__), tempest/student.py:75-79,
+//        tempest/tools.py:101-110 (volume_variation regularisation / inverse)
+#include "tb_common.cuh"
+
+namespace {
+using namespace tb;
+
+// in-place lower Cholesky of the d x d matrix in `A` (shared memory); returns false on a
+// non-positive / non-finite pivot (LAPACK potrf info > 0  <=>  np.linalg.LinAlgError)
+__device__ bool chol_lower(double* A, int d) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  for (int j = 0; j < d; ++j) {
+    if (threadIdx.x == 0) {
+      double s = A[j * d + j];
+      for (int k = 0; k < j; ++k) s -= A[j * d + k] * A[j * d + k];
+      if (!(s > 0.0) || !isfinite(s)) ok = 0; else A[j * d + j] = sqrt(s);
+    }
+    __syncthreads();
+    if (!ok) return false;
+    const double piv = A[j * d + j];
+    for (int i = j + 1 + threadIdx.x; i < d; i += blockDim.x) {
+      double s = A[i * d + j];
+      for (int k = 0; k < j; ++k) s -= A[i * d + k] * A[j * d + k];
+      A[i * d + j] = s / piv;
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(128)
+chol_inv_kernel(double* __restrict__ a, int d, double* __restrict__ chol, double* __restrict__ inv,
+                int* __restrict__ info, double* __restrict__ norms) {
+  extern __shared__ double sm[];
+  double* A = sm;            // working copy / L
+  double* Li = sm + d * d;   // L^{-1}
+  double* mat = a + (size_t)blockIdx.x * d * d;
+  __shared__ double red[40];
+  int status = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) A[e] = mat[e];
+    __syncthreads();
+    if (chol_lower(A, d)) break;
+    if (attempt == 1) { status = 2; break; }
+    // reg = max(1e-6, 1e-6 * |trace|) on the diagonal (modes.py:115-117), written back to `a`
+    double tr = 0.0;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) tr += mat[i * d + i];
+    tr = block_sum(tr, red);
+    const double reg = fmax(1e-6, 1e-6 * fabs(tr));
+    for (int i = threadIdx.x; i < d; i += blockDim.x) mat[i * d + i] += reg;
+    status = 1;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && info) info[blockIdx.x] = status;
+  if (status == 2) return;
+  // zero the strict upper triangle (np.linalg.cholesky returns a lower-triangular matrix)
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) { int i = e / d, j = e - i * d; if (j > i) A[e] = 0.0; }
+  __syncthreads();
+  if (chol) for (int e = threadIdx.x; e < d * d; e += blockDim.x) chol[(size_t)blockIdx.x * d * d + e] = A[e];
+  // L^{-1}: column c by forward substitution, one column per thread
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    for (int i = 0; i < d; ++i) {
+      if (i < c) { Li[i * d + c] = 0.0; continue; }
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= A[i * d + k] * Li[k * d + c];
+      Li[i * d + c] = s / A[i * d + i];
+    }
+  }
+  __syncthreads();
+  // inv = L^{-T} L^{-1}
+  double fro_inv = 0.0, fro_a = 0.0;
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e - i * d;
+    double s = 0.0;
+    const int k0 = i > j ? i : j;
+    for (int k = k0; k < d; ++k) s += Li[k * d + i] * Li[k * d + j];
+    if (inv) inv[(size_t)blockIdx.x * d * d + e] = s;
+    fro_inv += s * s;
+    const double av = mat[e];
+    fro_a += av * av;
+  }
+  fro_inv = block_sum(fro_inv, red);
+  fro_a = block_sum(fro_a, red);
+  double tr = 0.0;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) tr += mat[i * d + i];
+  tr = block_sum(tr, red);
+  if (threadIdx.x == 0 && norms) {
+    norms[blockIdx.x * 3 + 0] = sqrt(fro_a);
+    norms[blockIdx.x * 3 + 1] = sqrt(fro_inv);
+    norms[blockIdx.x * 3 + 2] = tr;
+  }
+}
+
+// Sigma = scatter/(M-1) * (M-1)/M + diag(scatter/M)/M   (student.py:63 with np.cov ddof=1, np.var ddof=0)
+__global__ void student_sigma_kernel(const double* __restrict__ scatter, int d, double m_total, double* __restrict__ sigma) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d * d; e += gridDim.x * blockDim.x) {
+    const int i = e / d, j = e - i * d;
+    const double s = scatter[e];
+    double v = ((s * (1.0 / (m_total - 1.0))) * (m_total - 1.0)) / m_total;   // np.cov multiplies by 1/(M-1)
+    if (i == j) v += (1.0 / m_total) * (s / m_total);
+    sigma[e] = v;
+  }
+}
+
+// mean of the two middle order statistics per column (np.median on an even count, student.py:62)
+__global__ void median_pair_kernel(const double* __restrict__ pair, int d, double* __restrict__ med) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < d) med[c] = (pair[2 * c] + pair[2 * c + 1]) * 0.5;
+}
+
+// cov += reg * I with reg = 1e-6 * trace(cov)   (tools.py:101-104)
+__global__ void add_trace_reg_kernel(double* __restrict__ cov, int d, double factor) {
+  __shared__ double tr;
+  if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < d; ++i) t += cov[i * d + i]; tr = t; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) cov[i * d + i] += factor * tr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tb_chol_inv(double* a, int32_t d, int32_t batch, double* chol, double* inv, int32_t* info, double* norms3,
+                tb_stream_t stream) {
+  if (!a || d <= 0 || d > 128 || batch <= 0) return TB_ERR_ARG;
+  const size_t smem = sizeof(double) * 2 * (size_t)d * d;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  chol_inv_kernel<<<batch, 128, smem, as_stream(stream)>>>(a, d, chol, inv, info, norms3);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_student_sigma(const double* scatter, int32_t d, double m_total, double* sigma, tb_stream_t stream) {
+  if (!scatter || !sigma || d <= 0 || m_total < 2.0) return TB_ERR_ARG;
+  student_sigma_kernel<<<(d * d + 255) / 256, 256, 0, as_stream(stream)>>>(scatter, d, m_total, sigma);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_median_pairs(const double* pair, int32_t d, double* med, tb_stream_t stream) {
+  if (!pair || !med || d <= 0) return TB_ERR_ARG;
+  median_pair_kernel<<<(d + 127) / 128, 128, 0, as_stream(stream)>>>(pair, d, med);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_add_trace_reg(double* cov, int32_t d, double factor, tb_stream_t stream) {
+  if (!cov || d <= 0) return TB_ERR_ARG;
+  add_trace_reg_kernel<<<1, 128, 0, as_stream(stream)>>>(cov, d, factor);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,436 @@
+// Fused mutation kernels (a14, a15).
+//   ref: tempest/steps/mutate.py:76-200 (warm-up draw, bookkeeping)
+//        tempest/mcmc.py:142-208 (step loop), :225-288 (tpCN), :301-323 (RWM),
+//        :104-135 (adaptive step count), :326-411 (boundaries)
+//
+// One thread per walker; one launch per Metropolis step.  A step proposes (Student-t scale,
+// Cholesky-preconditioned pCN or random-walk move, boundary map, redraw until inside the unit
+// cube), evaluates prior transform + likelihood in-kernel, accepts/rejects and leaves per-mode
+// partial sums; the last CTA folds them in a fixed order, adapts sigma_c and evaluates the stop
+// rule into a device-resident control block, so the next launch needs no host round trip (a
+// launch made after the stop rule fired returns immediately).
+// HBM traffic per step: the active set (u row, logl, q) is read once and written on accept;
+// proposals, normals and likelihood terms never leave registers.
+#include "tb_like.cuh"
+
+namespace {
+using namespace tb;
+
+constexpr int kMcmcBlock = 128;
+constexpr int kMaxModes = 64;
+constexpr int kMaxAttempts = 100000;
+
+// control block indices (doubles)
+enum { C_STEPS = 0, C_DONE = 1, C_NACC = 2, C_MEAN_ALPHA = 3, C_ERR = 4, C_NPROP = 5, C_SIGMA0 = 6, C_BASE = 8 };
+
+struct McmcWs {
+  unsigned int ticket;
+  unsigned int pad[3];
+  double partial[1];  // [grid][K+3]: sum alpha per mode, n accepted, n proposals, error flag
+};
+
+struct StepArgs {
+  int64_t n;
+  tb_mcmc_params p;
+  tb_tape tape;
+  const int32_t* assign;
+  double* u;
+  double* logl;
+  double* qcur;
+  McmcWs* ws;
+  double* ctrl;
+};
+
+__device__ __forceinline__ double bc_apply(double v, int kind) {
+  if (kind == 1) {                       // periodic: numpy float `% 1.0`
+    double m = fmod(v, 1.0);
+    if (m != 0.0) { if (m < 0.0) m += 1.0; } else m = 0.0;
+    return m;
+  }
+  if (kind == 2) {                       // reflective: floor-parity fold (mcmc.py:356-364)
+    const double fl = floor(v);
+    const double r = v - fl;
+    const long long k = (long long)fl;
+    return ((k & 1LL) == 0) ? r : 1.0 - r;
+  }
+  return v;
+}
+
+// fold the per-CTA partials, adapt sigma and evaluate the stop rule (mcmc.py:180-194, 104-135)
+__device__ void finish_step(const StepArgs& a, int K, int nparts) {
+  __shared__ double tot[kMaxModes + 3];
+  const int W = K + 3;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    double t = 0.0;
+    for (int b = 0; b < nparts; ++b) t += __ldcg(a.ws->partial + (size_t)b * W + c);
+    tot[c] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* ctrl = a.ctrl;
+    const int d = a.p.n_dim;
+    const int it = (int)ctrl[C_STEPS] + 1;
+    const double sigma0 = 2.38 / sqrt((double)d);
+    double* sigma = ctrl + C_BASE;
+    const double* count = ctrl + C_BASE + K;
+    double* salpha = ctrl + C_BASE + 2 * K;
+    double all_alpha = 0.0;
+    const double rate = 1.0 / (double)(it + 1);
+    for (int c = 0; c < K; ++c) {
+      salpha[c] = tot[c];
+      all_alpha += tot[c];
+      if (count[c] > 0.0) {
+        const double mean_alpha = tot[c] / count[c];
+        double s = sigma[c] + rate * (mean_alpha - 0.234);
+        if (a.p.sampler == TB_SAMPLE_TPCN) s = fmin(fmax(s, 0.0), fmin(sigma0, 0.99));
+        sigma[c] = s;
+      }
+    }
+    const double n_all = (double)a.p.n_global;
+    const double acc = tot[K] / n_all;
+    // weighted sigma over the first n_nonempty sigmas (reference quirk: sigmas[:len(sizes)])
+    double sw = 0.0, ws = 0.0;
+    int j = 0;
+    for (int c = 0; c < K; ++c) if (count[c] > 0.0) { ws += sigma[j] * count[c]; sw += count[c]; ++j; }
+    const double wsig = ws / sw;
+    const double n_min = (double)(a.p.n_steps * d);
+    const double ratio = sigma0 / fmax(1e-6, wsig);
+    const double n_adapt = (double)(a.p.n_steps * d) * (0.234 / fmax(0.01, acc)) * (ratio * ratio);
+    const double n_cap = (double)(a.p.n_max * d);
+    const double n_final = fmin(fmax(n_min, n_adapt), n_cap);
+    const int stop_at = (int)n_final;   // Python int() truncation
+    ctrl[C_STEPS] = (double)it;
+    ctrl[C_NACC] = tot[K];
+    ctrl[C_MEAN_ALPHA] = all_alpha / n_all;
+    ctrl[C_NPROP] += tot[K + 1];
+    if (tot[K + 2] != 0.0) ctrl[C_ERR] = tot[K + 2];
+    if (it >= stop_at || tot[K + 2] != 0.0) ctrl[C_DONE] = 1.0;
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kMcmcBlock)
+mcmc_step_kernel(StepArgs a) {
+  if (a.ctrl[C_DONE] != 0.0) return;
+  extern __shared__ double sm[];
+  const int d = a.p.n_dim, K = a.p.n_modes;
+  const bool tpcn = a.p.sampler == TB_SAMPLE_TPCN;
+  const int step = (int)a.ctrl[C_STEPS];          // steps completed so far
+  // stage mode statistics: mean[K][d], chol[K][d][d], inv[K][d][d], dof[K], sigma[K]
+  double* s_mean = sm;
+  double* s_chol = s_mean + K * d;
+  double* s_inv = s_chol + K * d * d;
+  double* s_dof = s_inv + K * d * d;
+  double* s_sig = s_dof + K;
+  double* s_part = s_sig + K;                      // [K+3] CTA partial sums
+  for (int e = threadIdx.x; e < K * d; e += blockDim.x) s_mean[e] = __ldg(a.p.mode_mean + e);
+  for (int e = threadIdx.x; e < K * d * d; e += blockDim.x) {
+    s_chol[e] = __ldg(a.p.mode_chol + e);
+    s_inv[e] = __ldg(a.p.mode_inv + e);
+  }
+  for (int e = threadIdx.x; e < K; e += blockDim.x) { s_dof[e] = __ldg(a.p.mode_dof + e); s_sig[e] = a.ctrl[C_BASE + e]; }
+  for (int e = threadIdx.x; e < K + 3; e += blockDim.x) s_part[e] = 0.0;
+  __syncthreads();
+
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double alpha = 0.0;
+  int accepted = 0, nprop = 0, err = 0, c = 0;
+  if (k < a.n) {
+    c = a.assign ? a.assign[k] : 0;
+    const double* mu = s_mean + c * d;
+    const double* L = s_chol + c * d * d;
+    const double* IV = s_inv + c * d * d;
+    const double sig = s_sig[c], dof = s_dof[c];
+    double u[DP], diff[DP], z[DP], prop[DP];
+    double* urow = a.u + k * d;
+#pragma unroll
+    for (int i = 0; i < DP; ++i) if (i < d) { u[i] = urow[i]; diff[i] = u[i] - mu[i]; }
+    const double logl = a.logl[k];
+    const uint64_t slot = (uint64_t)(a.p.slot_offset + k);
+    const Philox rng(a.p.seed, a.p.iteration);
+    const bool tape = a.p.rng_mode == TB_RNG_TAPE;
+    const int64_t tix = (int64_t)step * a.n + k;
+    if (tape && step >= a.tape.steps) err = 1;
+
+    double scale_s = 0.0, q = 0.0, keep = 0.0;
+    if (tpcn) {
+      q = a.qcur[k];
+      // s = 1 / Gamma(shape=(d+nu)/2, scale=2/(nu+q))   (mcmc.py:233-236)
+      double g;
+      if (tape) g = err ? 1.0 : a.tape.gamma[tix];
+      else {
+        // Marsaglia-Tsang (shape >= 1 always: d + nu >= 2)
+        const double shape = 0.5 * ((double)d + dof);
+        const double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+        g = dd;
+        for (uint32_t trial = 0; trial < 64; ++trial) {
+          double n0, n1, u0, u1;
+          philox_n2(rng, slot, (uint32_t)step, 0x800000u | trial, n0, n1);
+          philox_u2(rng, slot, (uint32_t)step, RNG_GAMMA, trial, u0, u1, true);
+          const double v1 = 1.0 + cc * n0;
+          if (v1 <= 0.0) continue;
+          const double v = v1 * v1 * v1;
+          if (log(u0) < 0.5 * n0 * n0 + dd - dd * v + dd * log(v)) { g = dd * v; break; }
+        }
+      }
+      const double gscale = 2.0 / (dof + q);
+      const double s = 1.0 / (gscale * g);
+      scale_s = sig * sqrt(s);
+      keep = sqrt(__dsub_rn(1.0, __dmul_rn(sig, sig)));
+    }
+    // propose until inside the cube (redraw z only; mcmc.py:239-249 / :306-312)
+    const int n_att_tape = tape && !err ? a.tape.z_cnt[tix] : 0;
+    const double* ztape = tape && !err ? a.tape.z + a.tape.z_off[tix] : nullptr;
+    bool inside = false;
+    int attempt = 0;
+    while (!inside && !err) {
+      if (tape) {
+        if (attempt >= n_att_tape) { err = 1; break; }
+#pragma unroll
+        for (int i = 0; i < DP; ++i) if (i < d) z[i] = ztape[attempt * d + i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < DP; i += 2) if (i < d) {
+          double z0, z1;
+          philox_n2(rng, slot, (uint32_t)step, (uint32_t)(attempt * ((DP + 1) / 2) + i / 2), z0, z1);
+          z[i] = z0;
+          if (i + 1 < DP) z[i + 1] = z1;
+        }
+      }
+      ++nprop;
+      inside = true;
+#pragma unroll
+      for (int i = 0; i < DP; ++i) if (i < d) {
+        double lz = 0.0;
+        const double cmul = tpcn ? scale_s : sig;
+        for (int j = 0; j <= i; ++j) lz += (cmul * L[i * d + j]) * z[j];
+        double v = tpcn ? ((mu[i] + keep * diff[i]) + lz) : (u[i] + lz);
+        const int kind = a.p.bc_kind ? a.p.bc_kind[i] : 0;
+        v = bc_apply(v, kind);
+        if (kind == 0 && !(v >= 0.0 && v <= 1.0)) inside = false;
+        prop[i] = v;
+      }
+      ++attempt;
+      if (attempt >= kMaxAttempts) { err = 2; break; }
+    }
+    if (!err) {
+      // prior transform + likelihood in registers
+      double x[DP];
+#pragma unroll
+      for (int i = 0; i < DP; ++i) if (i < d) x[i] = prior_affine(a.p.prior_params, d, i, prop[i]);
+      const double logl_new = eval_like(a.p.like_id, a.p.like_params, d, x);
+      double factor = 0.0, q_new = 0.0;
+      if (tpcn) {   // Student-t density ratio (mcmc.py:251-279)
+        double dn[DP];
+#pragma unroll
+        for (int i = 0; i < DP; ++i) if (i < d) dn[i] = prop[i] - mu[i];
+        for (int j = 0; j < d; ++j) {
+          double y = 0.0;
+          for (int i = 0; i < d; ++i) y += dn[i] * IV[i * d + j];
+          q_new += y * dn[j];
+        }
+        const double hd = -0.5 * ((double)d + dof);
+        const double A = hd * log(1.0 + q_new / dof);
+        const double B = hd * log(1.0 + q / dof);
+        factor = __dadd_rn(-A, B);
+      }
+      double al = exp(__dadd_rn(__dmul_rn(a.p.beta, __dsub_rn(logl_new, logl)), factor));
+      al = fmin(1.0, al);
+      if (isnan(al)) al = 0.0;
+      alpha = al;
+      double ur;
+      if (tape) ur = a.tape.acc_u[tix];
+      else { double dummy; philox_u2(rng, slot, (uint32_t)step, RNG_ACCEPT, 0, ur, dummy, false); }
+      if (ur < al) {
+        accepted = 1;
+#pragma unroll
+        for (int i = 0; i < DP; ++i) if (i < d) urow[i] = prop[i];
+        a.logl[k] = logl_new;
+        if (tpcn) a.qcur[k] = q_new;
+      }
+    }
+  }
+  // CTA partials: shared atomics would make the order run-dependent; use a fixed-order fold
+  __shared__ double fold[kMcmcBlock];
+  __shared__ int foldc[kMcmcBlock];
+  fold[threadIdx.x] = alpha;
+  foldc[threadIdx.x] = (k < a.n) ? c : -1;
+  __syncthreads();
+  for (int m = threadIdx.x; m < K; m += blockDim.x) {
+    double t = 0.0;
+    for (int i = 0; i < kMcmcBlock; ++i) if (foldc[i] == m) t += fold[i];
+    s_part[m] = t;
+  }
+  __shared__ double red[40];
+  const double nacc = block_sum((double)accepted, red);
+  const double npr = block_sum((double)nprop, red);
+  const double ner = block_max((double)err, red);
+  const int W = K + 3;
+  if (threadIdx.x == 0) { s_part[K] = nacc; s_part[K + 1] = npr; s_part[K + 2] = ner; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < W; e += blockDim.x) a.ws->partial[(size_t)blockIdx.x * W + e] = s_part[e];
+  if (last_block_arrives(&a.ws->ticket)) finish_step(a, K, gridDim.x);
+}
+
+// q_k = (u_k - mu_c)^T Sigma_c^{-1} (u_k - mu_c) for the initial state; per-mode walker counts; sigma init
+__global__ void __launch_bounds__(kMcmcBlock)
+mcmc_begin_kernel(int64_t n, tb_mcmc_params p, const int32_t* __restrict__ assign, const double* __restrict__ u,
+                  double* __restrict__ qcur, double* __restrict__ ctrl) {
+  const int d = p.n_dim, K = p.n_modes;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    const int c = assign ? assign[k] : 0;
+    if (qcur) {
+      const double* mu = p.mode_mean + c * d;
+      const double* IV = p.mode_inv + (size_t)c * d * d;
+      double q = 0.0;
+      for (int j = 0; j < d; ++j) {
+        double y = 0.0;
+        for (int i = 0; i < d; ++i) y += (u[k * d + i] - __ldg(mu + i)) * __ldg(IV + i * d + j);
+        q += y * (u[k * d + j] - __ldg(mu + j));
+      }
+      qcur[k] = q;
+    }
+    atomicAdd(ctrl + C_BASE + K + c, 1.0);   // exact: integer counts < 2^53
+  }
+}
+
+__global__ void mcmc_init_ctrl_kernel(tb_mcmc_params p, double* __restrict__ ctrl) {
+  const int K = p.n_modes;
+  const double sigma0 = 2.38 / sqrt((double)p.n_dim);
+  for (int e = threadIdx.x; e < C_BASE + 3 * K; e += blockDim.x) {
+    double v = 0.0;
+    if (e == C_SIGMA0) v = sigma0;
+    if (e >= C_BASE && e < C_BASE + K) v = (p.sampler == TB_SAMPLE_TPCN) ? fmin(sigma0, 0.99) : sigma0;  // mcmc.py:222-223, 298-299
+    ctrl[e] = v;
+  }
+}
+
+// warm-up: u ~ U(0,1)^d, x = prior(u), logl = L(x)   (mutate.py:100-105)
+__global__ void __launch_bounds__(kMcmcBlock)
+prior_draw_kernel(int64_t n, tb_mcmc_params p, const double* __restrict__ tape_u, const double* __restrict__ u_in,
+                  double* __restrict__ u, double* __restrict__ x, double* __restrict__ logl) {
+  const int d = p.n_dim;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const Philox rng(p.seed, p.iteration);
+  const uint64_t slot = (uint64_t)(p.slot_offset + k);
+  double xs[128];
+  for (int i = 0; i < d; i += 2) {
+    double a = 0.0, b = 0.0;
+    if (u_in) { a = u_in[k * d + i]; if (i + 1 < d) b = u_in[k * d + i + 1]; }
+    else if (tape_u) { a = tape_u[k * d + i]; if (i + 1 < d) b = tape_u[k * d + i + 1]; }
+    else philox_u2(rng, slot, 0u, RNG_PRIOR, (uint32_t)(i / 2), a, b, false);
+    if (u) u[k * d + i] = a;
+    xs[i] = prior_affine(p.prior_params, d, i, a);
+    if (i + 1 < d) { if (u) u[k * d + i + 1] = b; xs[i + 1] = prior_affine(p.prior_params, d, i + 1, b); }
+  }
+  if (x) for (int i = 0; i < d; ++i) x[k * d + i] = xs[i];
+  if (logl) logl[k] = eval_like(p.like_id, p.like_params, d, xs);
+}
+
+// uniforms for the host-driven resampling / training draws (same Philox stream family)
+__global__ void __launch_bounds__(kBlock)
+philox_uniform_kernel(uint64_t seed, uint64_t iteration, uint32_t purpose, int64_t offset, int64_t n,
+                      double* __restrict__ out) {
+  const Philox rng(seed, iteration);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double a, b;
+    philox_u2(rng, (uint64_t)(offset + i), 0u, purpose, 0u, a, b, false);
+    out[i] = a;
+  }
+}
+
+template <int DP>
+int launch_steps(const StepArgs& a, int count, cudaStream_t st) {
+  const int d = a.p.n_dim, K = a.p.n_modes;
+  const size_t smem = sizeof(double) * ((size_t)K * d + 2 * (size_t)K * d * d + 2 * K + K + 3);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mcmc_step_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int grid = (int)((a.n + kMcmcBlock - 1) / kMcmcBlock);
+  for (int s = 0; s < count; ++s) mcmc_step_kernel<DP><<<grid, kMcmcBlock, smem, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TB_OK : (int)e;
+}
+
+bool params_ok(int64_t n, const tb_mcmc_params* p) {
+  return p && n > 0 && p->n_dim > 0 && p->n_dim <= 128 && p->n_modes > 0 && p->n_modes <= kMaxModes &&
+         p->prior_params && p->like_params;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tb_mcmc_workspace_bytes(int64_t n, int32_t n_modes) {
+  const int64_t grid = (n + kMcmcBlock - 1) / kMcmcBlock;
+  return 256 + sizeof(double) * (size_t)grid * (n_modes + 3);
+}
+size_t tb_mcmc_ctrl_doubles(int32_t n_modes) { return C_BASE + 3 * (size_t)n_modes; }
+
+int tb_prior_draw(int64_t n, const tb_mcmc_params* p, const double* prior_u_tape, double* u, double* x,
+                  double* logl, tb_stream_t stream) {
+  if (!params_ok(n, p) || !u) return TB_ERR_ARG;
+  const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);
+  prior_draw_kernel<<<grid, kMcmcBlock, 0, as_stream(stream)>>>(n, *p, prior_u_tape, nullptr, u, x, logl);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_transform(const double* u, int64_t n, const tb_mcmc_params* p, double* x, double* logl, tb_stream_t stream) {
+  if (!params_ok(n, p) || !u) return TB_ERR_ARG;
+  const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);
+  prior_draw_kernel<<<grid, kMcmcBlock, 0, as_stream(stream)>>>(n, *p, nullptr, u, nullptr, x, logl);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t purpose, int64_t offset, int64_t n, double* out,
+                      tb_stream_t stream) {
+  if (n <= 0 || !out) return TB_ERR_ARG;
+  philox_uniform_kernel<<<stream_grid(n, kBlock, 16), kBlock, 0, as_stream(stream)>>>(seed, iteration, purpose,
+                                                                                     offset, n, out);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, const double* u, double* qcur,
+                  void* workspace, double* ctrl, tb_stream_t stream) {
+  if (!params_ok(n, p) || !u || !workspace || !ctrl) return TB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 16, st);
+  if (e != cudaSuccess) return (int)e;
+  mcmc_init_ctrl_kernel<<<1, 256, 0, st>>>(*p, ctrl);
+  const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);
+  mcmc_begin_kernel<<<grid, kMcmcBlock, 0, st>>>(n, *p, assign, u, p->sampler == TB_SAMPLE_TPCN ? qcur : nullptr, ctrl);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign, double* u,
+                  double* logl, double* qcur, void* workspace, double* ctrl, int32_t count, tb_stream_t stream) {
+  if (!params_ok(n, p) || !u || !logl || !workspace || !ctrl || count < 0) return TB_ERR_ARG;
+  if (p->sampler == TB_SAMPLE_TPCN && !qcur) return TB_ERR_ARG;
+  if (p->rng_mode == TB_RNG_TAPE && !tape) return TB_ERR_ARG;
+  StepArgs a;
+  a.n = n; a.p = *p;
+  if (tape) a.tape = *tape; else { a.tape.gamma = nullptr; a.tape.acc_u = nullptr; a.tape.z = nullptr;
+                                    a.tape.z_off = nullptr; a.tape.z_cnt = nullptr; a.tape.steps = 0; }
+  a.assign = assign; a.u = u; a.logl = logl; a.qcur = qcur; a.ws = (McmcWs*)workspace; a.ctrl = ctrl;
+  cudaStream_t st = as_stream(stream);
+  const int d = p->n_dim;
+  if (d <= 2) return launch_steps<2>(a, count, st);
+  if (d <= 4) return launch_steps<4>(a, count, st);
+  if (d <= 6) return launch_steps<6>(a, count, st);
+  if (d <= 8) return launch_steps<8>(a, count, st);
+  if (d <= 10) return launch_steps<10>(a, count, st);
+  if (d <= 16) return launch_steps<16>(a, count, st);
+  if (d <= 32) return launch_steps<32>(a, count, st);
+  if (d <= 64) return launch_steps<64>(a, count, st);
+  return launch_steps<128>(a, count, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+// Persistent-ensemble reweighting kernels (a1-a5).
+//   ref: tempest/state_manager.py:418-480 (compute_logw_and_logz)
+//        tempest/steps/reweight.py:88-297 (probe, ESS bracket, bisection)
+//        tempest/tools.py:120-135 (effective_sample_size)
+//
+// HBM layout: logl[N_total], C[N_total] fp64 SoA; per-generation scalars in tiny device arrays.
+// Probe = 16 B / particle streamed once (HBM-bound); the N_total x T log-sum-exp of the
+// reference is folded into the cached column C (fp64-pipe bound, done once per generation).
+#include "tb_common.cuh"
+
+namespace {
+using namespace tb;
+
+__device__ __forceinline__ double mix_term(double l, double b, double z, double ln) {
+  // (l*beta_t - logZ_t) + log n_t, rounded after every operation like numpy's temporaries
+  return __dadd_rn(__dsub_rn(__dmul_rn(l, b), z), ln);
+}
+
+__global__ void __launch_bounds__(kBlock)
+mixture_kernel(const double* __restrict__ logl, double* __restrict__ C, int64_t n_old, int64_t n_all,
+               const double* __restrict__ gb, const double* __restrict__ gz,
+               const double* __restrict__ gn, int T) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const double bT = __ldg(gb + T - 1), zT = __ldg(gz + T - 1), nT = __ldg(gn + T - 1);
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_all; s += stride) {
+    const double l = __ldg(logl + s);
+    if (s < n_old) {
+      C[s] = np_logaddexp(C[s], mix_term(l, bT, zT, nT));
+    } else {
+      double acc = mix_term(l, __ldg(gb), __ldg(gz), __ldg(gn));
+      for (int t = 1; t < T; ++t) acc = np_logaddexp(acc, mix_term(l, __ldg(gb + t), __ldg(gz + t), __ldg(gn + t)));
+      C[s] = acc;
+    }
+  }
+}
+
+// ---- probe -------------------------------------------------------------------------
+struct ProbeWs {            // workspace layout (device)
+  unsigned int ticket;      // last-block ticket
+  unsigned int barrier;     // grid barrier counter (next_beta)
+  unsigned int pad[2];
+  double partial[2][kMaxPartials][4];  // double-buffered {m, S1, S2, n_nonfinite}
+};
+
+__device__ __forceinline__ void probe_slice(const double* __restrict__ logl, const double* __restrict__ C,
+                                            int64_t n, double beta, Ess3& e, double& bad) {
+  // vectorised 2 x fp64 loads, 4 independent loads in flight per thread
+  const int64_t n2 = n >> 1;
+  const double2* l2 = reinterpret_cast<const double2*>(logl);
+  const double2* c2 = reinterpret_cast<const double2*>(C);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n2; i += 2 * stride) {
+    double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
+    double2 lb = __ldg(l2 + i + stride), cb = __ldg(c2 + i + stride);
+    double a0 = __dsub_rn(__dmul_rn(la.x, beta), ca.x), a1 = __dsub_rn(__dmul_rn(la.y, beta), ca.y);
+    double a2 = __dsub_rn(__dmul_rn(lb.x, beta), cb.x), a3 = __dsub_rn(__dmul_rn(lb.y, beta), cb.y);
+    bad += (double)(!isfinite(a0)) + (double)(!isfinite(a1)) + (double)(!isfinite(a2)) + (double)(!isfinite(a3));
+    e.push(a0); e.push(a1); e.push(a2); e.push(a3);
+  }
+  for (; i < n2; i += stride) {
+    double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
+    double a0 = __dsub_rn(__dmul_rn(la.x, beta), ca.x), a1 = __dsub_rn(__dmul_rn(la.y, beta), ca.y);
+    bad += (double)(!isfinite(a0)) + (double)(!isfinite(a1));
+    e.push(a0); e.push(a1);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double a0 = __dsub_rn(__dmul_rn(logl[n - 1], beta), C[n - 1]);
+    bad += (double)(!isfinite(a0));
+    e.push(a0);
+  }
+}
+
+// merge `nb` published partials in a fixed order; result identical in every caller
+__device__ __forceinline__ void merge_partials(const double (*part)[4], int nb, double* smem,
+                                               Ess3& e, double& bad) {
+  e.init();
+  bad = 0.0;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    // L2 loads: the partials were published by other SMs
+    e.merge(__ldcg(&part[b][0]), __ldcg(&part[b][1]), __ldcg(&part[b][2]));
+    bad += __ldcg(&part[b][3]);
+  }
+  block_merge_ess3(e, smem);
+  bad = block_sum(bad, smem + 100);
+}
+
+__device__ __forceinline__ void write_probe_result(double* out, const Ess3& e, double bad) {
+  out[0] = e.m; out[1] = e.s1; out[2] = e.s2;
+  out[3] = (e.s1 * e.s1) / e.s2;      // ESS = 1 / sum (w/S1)^2
+  out[4] = e.m + log(e.s1);           // logZ(beta) = LSE_s(a_s)   (log N_total cancels, :475)
+  out[5] = bad;
+}
+
+__global__ void __launch_bounds__(kBlock)
+probe_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n, double beta,
+             ProbeWs* ws, double* __restrict__ out) {
+  __shared__ double smem[160];
+  Ess3 e; e.init();
+  double bad = 0.0;
+  probe_slice(logl, C, n, beta, e, bad);
+  block_merge_ess3(e, smem);
+  bad = block_sum(bad, smem + 100);
+  if (threadIdx.x == 0) {
+    double* p = ws->partial[0][blockIdx.x];
+    p[0] = e.m; p[1] = e.s1; p[2] = e.s2; p[3] = bad;
+  }
+  if (last_block_arrives(&ws->ticket)) {
+    merge_partials(ws->partial[0], gridDim.x, smem, e, bad);
+    if (threadIdx.x == 0) write_probe_result(out, e, bad);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+weights_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n, double beta,
+               const double* __restrict__ stats, double* __restrict__ w, int want_log) {
+  const double m = stats[0], s1 = stats[1];
+  const double lse = stats[4];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
+    double a = __dsub_rn(__dmul_rn(__ldg(logl + s), beta), __ldg(C + s));
+    w[s] = want_log ? (a - lse) : exp(a - m) / s1;
+  }
+}
+
+// ---- device-side next-beta search ---------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int nb = gridDim.x;
+    unsigned int old = atomicAdd(counter, 1u);
+    unsigned int target = (old / nb + 1u) * nb;
+    while (*((volatile unsigned int*)counter) < target) { __nanosleep(20); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+constexpr double kBetaTol = 1e-4, kBetaRtol = 1e-8, kEssTol = 0.01, kMetricAtol = 0.5;  // config.py:233-236
+constexpr int kMaxBisect = 200;                                                          // reweight.py:121
+constexpr double kTiny = 2.2250738585072014e-308;
+
+__global__ void __launch_bounds__(kBlock)
+next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n,
+                 double beta_prev, double target, int flags, ProbeWs* ws, double* __restrict__ result,
+                 double* __restrict__ plog, int plog_cap) {
+  __shared__ double smem[160];
+  __shared__ double sh_beta;
+  __shared__ int sh_done;
+  // search state, replicated bit-identically in thread 0 of every CTA
+  int phase = (flags & 1) ? 1 : 0;   // 0: probe beta_prev, 1: probe 1.0, 2: bracket, 3: bisect
+  double lo = beta_prev, hi = 1.0, bmin = beta_prev, bmax = 1.0;
+  int nprobe = 0, nbis = 0, same = 0;
+  double beta = (phase == 0) ? beta_prev : 1.0;
+  for (;;) {
+    Ess3 e; e.init();
+    double bad = 0.0;
+    probe_slice(logl, C, n, beta, e, bad);
+    block_merge_ess3(e, smem);
+    bad = block_sum(bad, smem + 100);
+    const int buf = nprobe & 1;
+    if (threadIdx.x == 0) {
+      double* p = ws->partial[buf][blockIdx.x];
+      p[0] = e.m; p[1] = e.s1; p[2] = e.s2; p[3] = bad;
+    }
+    grid_barrier(&ws->barrier);
+    merge_partials(ws->partial[buf], gridDim.x, smem, e, bad);
+    if (threadIdx.x == 0) {
+      double ess = (e.s1 * e.s1) / e.s2;
+      if (blockIdx.x == 0 && plog != nullptr && nprobe < plog_cap) { plog[2 * nprobe] = beta; plog[2 * nprobe + 1] = ess; }
+      ++nprobe;
+      int done = 0;
+      double next = beta;
+      if (phase == 0) {                       // reweight.py:264-266
+        if (ess <= target) { done = 1; same = 1; }
+        else { phase = 1; next = 1.0; }
+      } else if (phase == 1) {                // :269-271
+        if (ess >= target) { done = 1; same = 1; }
+        else phase = 2;
+      } else if (phase == 2) {                // :288-295
+        if (ess >= target) lo = beta; else hi = beta;
+      } else {                                // :165-211
+        double val = isfinite(ess) ? ess : 1e10;
+        bool metric_ok = fabs(val - target) < fmax(kEssTol * fabs(target), kMetricAtol);
+        double scale = fmax(fmax(fabs(bmin), fabs(bmax)), kTiny);
+        bool beta_ok = (bmax - bmin) < fmax(kBetaRtol * scale, kBetaTol * scale);
+        ++nbis;
+        if (metric_ok || beta_ok || beta == 1.0 || nbis >= kMaxBisect) done = 1;
+        else if (val < target) bmax = beta; else bmin = beta;
+      }
+      if (!done && phase == 2) {              // :277-287
+        double mid = (hi + lo) * 0.5;
+        double scale = fmax(fmax(fabs(lo), fabs(hi)), kTiny);
+        if (hi - lo <= fmax(kBetaRtol * scale, kBetaTol * scale)) {
+          phase = 3; bmin = beta_prev; bmax = hi;   // bisect on [beta_prev, beta_high] (:409-414)
+        } else next = mid;
+      }
+      if (!done && phase == 3) next = (bmax + bmin) * 0.5;
+      if (done && blockIdx.x == 0) {
+        result[0] = beta; result[1] = e.m; result[2] = e.s1; result[3] = e.s2; result[4] = ess;
+        result[5] = e.m + log(e.s1); result[6] = (double)nprobe; result[7] = (double)same;
+        result[8] = bad;
+      }
+      sh_beta = next;
+      sh_done = done;
+    }
+    __syncthreads();
+    if (sh_done) break;
+    beta = sh_beta;
+    // thread 0 keeps the authoritative state; other threads only need beta / nprobe parity
+    if (threadIdx.x != 0) ++nprobe;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tb_version(void) { return 100; }
+int tb_sm_count(void) { return tb::sm_count(); }
+
+int tb_mixture_build(const double* logl, double* C, int64_t n_total, const double* gb, const double* gz,
+                     const double* gn, int32_t T, tb_stream_t stream) {
+  if (n_total < 0 || T <= 0 || (n_total > 0 && (!logl || !C))) return TB_ERR_ARG;
+  if (n_total == 0) return TB_OK;
+  int grid = stream_grid(n_total, kBlock, 16);
+  mixture_kernel<<<grid, kBlock, 0, as_stream(stream)>>>(logl, C, 0, n_total, gb, gz, gn, T);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_mixture_append(const double* logl, double* C, int64_t n_old, int64_t n_new, const double* gb,
+                      const double* gz, const double* gn, int32_t T_new, tb_stream_t stream) {
+  if (n_old < 0 || n_new < 0 || T_new <= 0) return TB_ERR_ARG;
+  if (n_old + n_new == 0) return TB_OK;
+  int grid = stream_grid(n_old + n_new, kBlock, 16);
+  mixture_kernel<<<grid, kBlock, 0, as_stream(stream)>>>(logl, C, n_old, n_old + n_new, gb, gz, gn, T_new);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+size_t tb_probe_workspace_bytes(void) { return sizeof(ProbeWs); }
+size_t tb_next_beta_workspace_bytes(void) { return sizeof(ProbeWs); }
+
+int tb_probe(const double* logl, const double* C, int64_t n, double beta, void* workspace, double* out6,
+             tb_stream_t stream) {
+  if (n <= 0 || !logl || !C || !workspace || !out6) return TB_ERR_ARG;
+  // 2 particles per thread per load; 4 CTAs of 256 threads per SM keep >= 32 x 16 B loads in flight per SM
+  int grid = stream_grid(n, kBlock * 4, 4);
+  probe_kernel<<<grid, kBlock, 0, as_stream(stream)>>>(logl, C, n, beta, (ProbeWs*)workspace, out6);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_weights(const double* logl, const double* C, int64_t n, double beta, const double* stats, double* w,
+               tb_stream_t stream) {
+  if (n <= 0 || !logl || !C || !stats || !w) return TB_ERR_ARG;
+  int grid = stream_grid(n, kBlock, 16);
+  weights_kernel<<<grid, kBlock, 0, as_stream(stream)>>>(logl, C, n, beta, stats, w, 0);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_log_weights(const double* logl, const double* C, int64_t n, double beta, const double* stats,
+                   double* logw, tb_stream_t stream) {
+  if (n <= 0 || !logl || !C || !stats || !logw) return TB_ERR_ARG;
+  int grid = stream_grid(n, kBlock, 16);
+  weights_kernel<<<grid, kBlock, 0, as_stream(stream)>>>(logl, C, n, beta, stats, logw, 1);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_next_beta(const double* logl, const double* C, int64_t n, double beta_prev, double ess_target,
+                 int32_t flags, void* workspace, double* result, double* probe_log, int32_t probe_log_cap,
+                 tb_stream_t stream) {
+  if (n <= 0 || !logl || !C || !workspace || !result) return TB_ERR_ARG;
+  static int max_coresident = 0;
+  if (max_coresident == 0) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, next_beta_kernel, kBlock, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) return TB_ERR_UNSUPPORTED;
+    max_coresident = per_sm * tb::sm_count();
+    if (max_coresident > kMaxPartials) max_coresident = kMaxPartials;
+  }
+  int64_t need = (n + kBlock * 4 - 1) / (kBlock * 4);
+  int grid = (int)(need < max_coresident ? need : max_coresident);
+  if (grid < 1) grid = 1;
+  ProbeWs* ws = (ProbeWs*)workspace;
+  cudaError_t e = cudaMemsetAsync(&ws->barrier, 0, sizeof(unsigned int), as_stream(stream));
+  if (e != cudaSuccess) return (int)e;
+  void* args[] = {(void*)&logl, (void*)&C, (void*)&n, (void*)&beta_prev, (void*)&ess_target, (void*)&flags,
+                  (void*)&ws, (void*)&result, (void*)&probe_log, (void*)&probe_log_cap};
+  e = cudaLaunchCooperativeKernel((void*)next_beta_kernel, dim3(grid), dim3(kBlock), args, 0, as_stream(stream));
+  if (e != cudaSuccess) return (int)e;
+  return TB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,653 @@
+"""Device implementations of the four Persistent Sampling steps.
+
+Mirrors ``Reweighter / Trainer / Resampler / Mutator .run()`` of the reference
+(tempest/steps/{reweight,train,resample,mutate}.py) -- same state keys written, same
+constants, same branch logic -- with every array operation executed by libtempest_b200
+kernels through the C ABI.  Host code only sequences kernels and takes the scalar decisions
+the reference takes in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import (BETA_RTOL, BETA_TOLERANCE, DOF_FALLBACK, ESS_TOLERANCE, MAX_BISECTION_ITERATIONS,
+                     METRIC_ATOL, METRIC_ATOL_CV, TRIM_BINS, TRIM_ESS)
+from .ensemble import PersistentEnsemble, ptr, stream_ptr
+
+_TINY = float(np.finfo(float).tiny)
+_EPS = float(np.finfo(float).eps)
+F64 = torch.float64
+
+
+class Workspace:
+    """Reusable device scratch (the C ABI never allocates)."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.lib = _lib.load()
+        self._buf = {}
+
+    def bytes(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self._buf.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._buf[name] = t
+        return t
+
+    def f64(self, name: str, n: int) -> torch.Tensor:
+        t = self._buf.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(int(n * 1.5), 16), dtype=F64, device=self.device)
+            self._buf[name] = t
+        return t[:n]
+
+    def i64(self, name: str, n: int) -> torch.Tensor:
+        t = self._buf.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(int(n * 1.5), 16), dtype=torch.int64, device=self.device)
+            self._buf[name] = t
+        return t[:n]
+
+    def i32(self, name: str, n: int) -> torch.Tensor:
+        t = self._buf.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(int(n * 1.5), 16), dtype=torch.int32, device=self.device)
+            self._buf[name] = t
+        return t[:n]
+
+
+# ======================================================================================
+# numpy arithmetic the reference relies on, restated for the host-side scalar decisions
+# ======================================================================================
+def numpy_pairwise_sum_equal(value: float, n: int) -> float:
+    """``np.sum(np.full(n, value))`` without materialising the array: numpy's pairwise
+    summation (8 running lanes over blocks of <= 128, halves split at ``n/2 - (n/2) % 8``)."""
+    memo = {}
+
+    def rec(m: int) -> float:
+        if m in memo:
+            return memo[m]
+        if m < 8:
+            r = 0.0
+            for _ in range(m):
+                r += value
+        elif m <= 128:
+            lanes = [value] * 8
+            i = 8
+            while i < m - (m % 8):
+                for j in range(8):
+                    lanes[j] += value
+                i += 8
+            r = ((lanes[0] + lanes[1]) + (lanes[2] + lanes[3])) + ((lanes[4] + lanes[5]) + (lanes[6] + lanes[7]))
+            while i < m:
+                r += value
+                i += 1
+        else:
+            m2 = m // 2
+            m2 -= m2 % 8
+            r = rec(m2) + rec(m - m2)
+        memo[m] = r
+        return r
+
+    return rec(int(n))
+
+
+def uniform_weights_ess(n: int) -> float:
+    """ESS the reference computes for ``n`` exactly equal weights (warm-up):
+    ``w = ones(n)``; ``w / np.sum(w)``; ``1 / np.sum(w**2)`` (tools.py:134-135).  Equals ``n``
+    only when the roundings cancel -- e.g. n = 42 gives 42.000000000000007 and the reference
+    then leaves the warm-up one generation early, so the branch must see the same value."""
+    wn = 1.0 / float(n)        # np.sum(ones(n)) is exact
+    return 1.0 / numpy_pairwise_sum_equal(wn * wn, n)
+
+
+def percentile_position(n: int, p: float) -> Tuple[int, int, float]:
+    """numpy ``percentile(..., method='linear')`` virtual index -> (lo, hi, gamma)."""
+    v = (n - 1) * (p / 100.0)
+    lo = int(math.floor(v))
+    g = v - lo
+    hi = min(lo + 1, n - 1)
+    lo = min(max(lo, 0), n - 1)
+    return lo, hi, g
+
+
+def numpy_lerp(a: float, b: float, t: float) -> float:
+    """numpy ``_lerp``: ``a + (b-a) t`` switched to ``b - (b-a)(1-t)`` for t >= 0.5."""
+    diff = b - a
+    if t >= 0.5:
+        return b - diff * (1 - t)
+    return a + diff * t
+
+
+# ======================================================================================
+# shared device helpers
+# ======================================================================================
+class Kernels:
+    """Thin typed wrappers over the C ABI bound to one device / workspace."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.lib = _lib.load()
+        self.ws = Workspace(device)
+        self._probe_ws = self.ws.bytes("probe", self.lib.tb_probe_workspace_bytes())
+        self._reduce_ws = self.ws.bytes("reduce", self.lib.tb_reduce_workspace_bytes())
+        self.probe_out = torch.zeros(16, dtype=F64, device=device)
+        self.n_probe_launches = 0
+
+    # -- reweighting ----------------------------------------------------------------------
+    def probe(self, ens: PersistentEnsemble, beta: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = self.probe_out if out is None else out
+        _lib.check(self.lib.tb_probe(ptr(ens.logl), ptr(ens.C), ens.n_total, float(beta), ptr(self._probe_ws),
+                                     ptr(out), stream_ptr()), "tb_probe")
+        self.n_probe_launches += 1
+        return out
+
+    def next_beta(self, ens: PersistentEnsemble, beta_prev: float, target: float, flags: int,
+                  log_cap: int = 512):
+        res = self.ws.f64("nb_res", 16)
+        plog = self.ws.f64("nb_log", 2 * log_cap)
+        _lib.check(self.lib.tb_next_beta(ptr(ens.logl), ptr(ens.C), ens.n_total, float(beta_prev), float(target),
+                                         int(flags), ptr(self._probe_ws), ptr(res), ptr(plog), log_cap,
+                                         stream_ptr()), "tb_next_beta")
+        return res, plog
+
+    def weights(self, ens: PersistentEnsemble, beta: float, stats: torch.Tensor, out: torch.Tensor, log=False):
+        fn = self.lib.tb_log_weights if log else self.lib.tb_weights
+        _lib.check(fn(ptr(ens.logl), ptr(ens.C), ens.n_total, float(beta), ptr(stats), ptr(out), stream_ptr()),
+                   "tb_weights")
+        return out
+
+    # -- moments / cv -------------------------------------------------------------------
+    def volume_variation(self, u: torch.Tensor, w: torch.Tensor, n: int, d: int) -> float:
+        """tools.py:58-117 on the device (w already normalised)."""
+        if n < d + 1:
+            return 1e10
+        ws = self.ws.bytes("mom", self.lib.tb_moments_workspace_bytes(d))
+        mean = self.ws.f64("vv_mean", d)
+        cov = self.ws.f64("vv_cov", d * d)
+        _lib.check(self.lib.tb_weighted_moments(ptr(u), ptr(w), n, d, ptr(ws), ptr(mean), ptr(cov), stream_ptr()),
+                   "tb_weighted_moments")
+        work = self.ws.f64("vv_work", d * d)
+        inv = self.ws.f64("vv_inv", d * d)
+        info = self.ws.i32("vv_info", 1)
+        norms = self.ws.f64("vv_norms", 3)
+        for attempt in range(2):
+            work.copy_(cov)
+            _lib.check(self.lib.tb_chol_inv(ptr(work), d, 1, None, ptr(inv), ptr(info), ptr(norms), stream_ptr()),
+                       "tb_chol_inv")
+            code = int(info.item())
+            nr = norms.cpu().numpy()
+            # matrix_rank(cov) < d  <=>  cond_2 >= 1/(d*eps); |A|_F |A^-1|_F >= cond_2 screens it
+            if attempt == 0:
+                singular = code != 0 or not np.isfinite(nr[:2]).all() or nr[0] * nr[1] >= 1.0 / (d * _EPS)
+            else:
+                singular = code == 2 or not np.isfinite(nr[:2]).all()   # np.linalg.inv raised (tools.py:108-110)
+            if not singular:
+                break
+            if attempt == 1:
+                return 1e10
+            _lib.check(self.lib.tb_add_trace_reg(ptr(cov), d, 1e-6, stream_ptr()), "tb_add_trace_reg")
+        out = self.ws.f64("vv_out", 1)
+        _lib.check(self.lib.tb_mahalanobis_cv(ptr(u), ptr(w), n, d, ptr(mean), ptr(inv), ptr(self._reduce_ws),
+                                              ptr(out), stream_ptr()), "tb_mahalanobis_cv")
+        return float(out.item())
+
+    # -- resampling -----------------------------------------------------------------------
+    def cdf(self, p: torch.Tensor, n: int, name: str = "cdf") -> torch.Tensor:
+        out = self.ws.f64(name, n)
+        ws = self.ws.bytes("cdf_ws", self.lib.tb_cdf_workspace_bytes(n))
+        _lib.check(self.lib.tb_cdf_exact(ptr(p), n, ptr(out), ptr(ws), stream_ptr()), "tb_cdf_exact")
+        return out
+
+    def search_right(self, cdf: torch.Tensor, n: int, draws: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        _lib.check(self.lib.tb_search_right(ptr(cdf), n, ptr(draws), draws.numel(), ptr(out), stream_ptr()),
+                   "tb_search_right")
+        return out
+
+    def systematic(self, cdf: torch.Tensor, n: int, u0: float, m: int, out: torch.Tensor) -> torch.Tensor:
+        flag = self.ws.i32("syst_flag", 1)
+        _lib.check(self.lib.tb_systematic(ptr(cdf), n, float(u0), m, ptr(out), ptr(flag), stream_ptr()),
+                   "tb_systematic")
+        if int(flag.item()):
+            raise IndexError("systematic resampling walked past the last weight (tools.py:223-225)")
+        return out
+
+    # -- trim_weights (tools.py:10-55) ------------------------------------------------------
+    def trim(self, w: torch.Tensor, n: int, ess: float = TRIM_ESS, bins: int = TRIM_BINS):
+        """Normalises ``w`` IN PLACE (tools.py:36) and returns (idx int64[n_trim], w_trim[n_trim]).
+
+        The reference scans i = bins-1 .. 0, each time thresholding at np.percentile(w, p_i) and
+        stopping at the first i whose trimmed ESS ratio reaches ``ess``.  The ratio is monotone in
+        the threshold, so the same i is found by (1) one binade histogram pass that brackets the
+        flip, (2) exact evaluations (radix order statistics + masked sums) of the few percentile
+        grid points inside the bracket, by bisection."""
+        lib = self.lib
+        st = stream_ptr()
+        stats = self.ws.f64("trim_stats", 3)
+        _lib.check(lib.tb_normalize_inplace(ptr(w), n, ptr(self._reduce_ws), ptr(stats), st), "tb_normalize_inplace")
+        cnt = self.ws.i64("trim_cnt", 2048)
+        s1 = self.ws.f64("trim_s1", 2048)
+        s2 = self.ws.f64("trim_s2", 2048)
+        _lib.check(lib.tb_binade_hist(ptr(w), n, ptr(cnt), ptr(s1), ptr(s2), st), "tb_binade_hist")
+        h_stats = stats.cpu().numpy()
+        h_cnt = cnt.cpu().numpy().astype(np.int64)
+        h_s1 = s1.cpu().numpy()
+        h_s2 = s2.cpu().numpy()
+        ess_total = 1.0 / h_stats[1]
+        # suffix sums over binades (threshold at the lower edge of binade b keeps bins >= b)
+        s1_ge = np.cumsum(h_s1[::-1])[::-1]
+        s2_ge = np.cumsum(h_s2[::-1])[::-1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = (s1_ge * s1_ge / s2_ge) / ess_total
+        ok_edge = np.nan_to_num(ratio, nan=0.0) >= ess
+        bstar = int(np.max(np.nonzero(ok_edge)[0]))          # highest binade edge that still passes
+        cnt_lt = np.concatenate([[0], np.cumsum(h_cnt)])      # elements in bins < b
+        percentiles = np.linspace(0, 99, bins)
+        pos = [percentile_position(n, float(p)) for p in percentiles]
+        lo_arr = np.array([p[0] for p in pos], dtype=np.int64)
+        hi_arr = np.array([p[1] for p in pos], dtype=np.int64)
+        bin_lo = np.searchsorted(cnt_lt, lo_arr, side="right") - 1
+        bin_hi = np.searchsorted(cnt_lt, hi_arr, side="right") - 1
+        sure_true = bin_hi < bstar
+        sure_false = bin_lo > bstar
+        amb = np.nonzero(~sure_true & ~sure_false)[0]
+        best = int(np.max(np.nonzero(sure_true)[0])) if sure_true.any() else 0
+        cand = np.union1d(amb, [best]).astype(np.int64)   # grid points that may need an exact evaluation
+
+        cache = {}
+        comp = None  # (values tensor, count, n_below)
+
+        def exact(i: int):
+            nonlocal comp
+            if i in cache:
+                return cache[i]
+            if comp is None:
+                # compact everything from the lowest binade a candidate threshold can touch
+                b0 = int(bin_lo[cand].min())
+                if b0 <= 0:
+                    comp = (w, n, 0)
+                else:
+                    edge = float(np.ldexp(1.0, b0 - 1023))
+                    wc = self.ws.f64("trim_comp", n)
+                    nout = self.ws.i64("trim_nout", 1)
+                    cws = self.ws.bytes("compact", lib.tb_compact_workspace_bytes(n))
+                    _lib.check(lib.tb_compact_ge(ptr(w), n, edge, 1.0, ptr(cws), None, ptr(wc), ptr(nout), st),
+                               "tb_compact_ge")
+                    m = int(nout.item())
+                    comp = (wc, m, n - m)
+            vals, m, below = comp
+            lo, hi, g = pos[i]
+            ranks = self.ws.i64("trim_ranks", 2)
+            ranks.copy_(torch.tensor([lo - below, hi - below], dtype=torch.int64))
+            sel = self.ws.f64("trim_sel", 2)
+            sws = self.ws.bytes("select", lib.tb_select_workspace_bytes(1, 2))
+            _lib.check(lib.tb_select_ranks(ptr(vals), None, 1, m, 1, None, ptr(ranks), 2, ptr(sws), ptr(sel), st),
+                       "tb_select_ranks")
+            a, b = sel.cpu().numpy()
+            thr = numpy_lerp(float(a), float(b), g)
+            out3 = self.ws.f64("trim_m3", 3)
+            _lib.check(lib.tb_masked_sums(ptr(vals), m, thr, ptr(self._reduce_ws), ptr(out3), st), "tb_masked_sums")
+            c, a1, a2 = out3.cpu().numpy()
+            good = ((a1 * a1 / a2) / ess_total) >= ess
+            cache[i] = (bool(good), thr)
+            return cache[i]
+
+        chosen = best
+        lo_i, hi_i = 0, amb.size - 1              # largest ambiguous grid point that passes (monotone)
+        while lo_i <= hi_i:
+            mid = (lo_i + hi_i) // 2
+            if exact(int(amb[mid]))[0]:
+                chosen = int(amb[mid])
+                lo_i = mid + 1
+            else:
+                hi_i = mid - 1
+        thr = exact(chosen)[1]
+        # final: deterministic sum over the kept set on the full array, then ordered compaction
+        out3 = self.ws.f64("trim_m3", 3)
+        _lib.check(lib.tb_masked_sums(ptr(w), n, thr, ptr(self._reduce_ws), ptr(out3), st), "tb_masked_sums")
+        c, a1, _ = out3.cpu().numpy()
+        n_trim = int(c)
+        idx = torch.empty(n_trim, dtype=torch.int64, device=self.device)
+        wt = torch.empty(n_trim, dtype=F64, device=self.device)
+        nout = self.ws.i64("trim_nout", 1)
+        cws = self.ws.bytes("compact", lib.tb_compact_workspace_bytes(n))
+        _lib.check(lib.tb_compact_ge(ptr(w), n, thr, float(a1), ptr(cws), ptr(idx), ptr(wt), ptr(nout), st),
+                   "tb_compact_ge")
+        self.last_trim = dict(bin=chosen, threshold=thr, n_trim=n_trim, n_exact=len(cache))
+        return idx, wt
+
+
+class ModeStats:
+    """Device mirror of ``ModeStatistics`` (tempest/modes.py:58-119): per-mode mean, covariance,
+    dof, lower Cholesky factor and inverse, all resident in HBM."""
+
+    def __init__(self, means: torch.Tensor, covs: torch.Tensor, chol: torch.Tensor, inv: torch.Tensor,
+                 dofs: torch.Tensor):
+        self.means, self.covariances, self.chol_covariances, self.inv_covariances = means, covs, chol, inv
+        self.degrees_of_freedom = dofs
+
+    @property
+    def K(self) -> int:
+        return int(self.means.shape[0])
+
+    @property
+    def n_dim(self) -> int:
+        return int(self.means.shape[1])
+
+    @classmethod
+    def identity(cls, d: int, device) -> "ModeStats":
+        eye = torch.eye(d, dtype=F64, device=device).reshape(1, d, d)
+        return cls(torch.zeros((1, d), dtype=F64, device=device), eye.clone(), eye.clone(), eye.clone(),
+                   torch.full((1,), DOF_FALLBACK, dtype=F64, device=device))
+
+
+# ======================================================================================
+# The four steps
+# ======================================================================================
+class Reweighter:
+    """steps/reweight.py:341-495."""
+
+    def __init__(self, core):
+        self.core = core
+        cfg = core.config
+        self.n_particles = cfg.n_particles
+        self.ess_ratio = cfg.ess_ratio
+        self.volume_variation = cfg.volume_variation
+        self.device_search = True     # tb_next_beta (one launch) vs host-driven probes
+        self.probe_log: List[Tuple[float, float]] = []
+
+    # one probe: returns (ess, metric) and leaves (m, S1, ...) in core.k.probe_out
+    def _probe(self, beta: float) -> Tuple[float, float]:
+        core = self.core
+        ens = core.ensemble
+        out = core.k.probe(ens, beta).cpu().numpy()
+        ess = float(out[3])
+        if core.warmup_regime and beta == 0.0:
+            ess = uniform_weights_ess(ens.n_total)
+        metric = ess
+        if self.volume_variation is not None:
+            w = core.k.weights(ens, beta, core.k.probe_out, core.weights_buffer())
+            metric = core.k.volume_variation(ens.u, w, ens.n_total, ens.n_dim)
+        self.probe_log.append((float(beta), ess))
+        return ess, metric
+
+    def _ess_bracket(self, beta_current: float, target: float) -> Tuple[float, float]:
+        lo, hi = beta_current, 1.0
+        ess_cur, _ = self._probe(beta_current)
+        if ess_cur <= target:                      # reweight.py:264-266
+            return beta_current, beta_current
+        ess_one, _ = self._probe(1.0)
+        if ess_one >= target:                      # :269-271
+            return 1.0, 1.0
+        while True:                                # :277-295
+            mid = (hi + lo) * 0.5
+            scale = max(abs(lo), abs(hi), _TINY)
+            if hi - lo <= max(BETA_RTOL * scale, BETA_TOLERANCE * scale):
+                break
+            ess_mid, _ = self._probe(mid)
+            if ess_mid >= target:
+                lo = mid
+            else:
+                hi = mid
+        return lo, hi
+
+    def _bisect(self, beta_min: float, beta_max: float, target: float, use_metric: bool):
+        dynamic = self.volume_variation is not None
+        beta = beta_min
+        ess = float("nan")
+        for _ in range(MAX_BISECTION_ITERATIONS):  # reweight.py:162-223
+            beta = (beta_max + beta_min) * 0.5
+            ess, metric = self._probe(beta)
+            val = metric if use_metric else ess
+            if not math.isfinite(val):
+                val = 1e10
+            atol = METRIC_ATOL_CV if dynamic else METRIC_ATOL
+            metric_ok = abs(val - target) < max(ESS_TOLERANCE * abs(target), atol)
+            scale = max(abs(beta_min), abs(beta_max), _TINY)
+            beta_ok = (beta_max - beta_min) < max(BETA_RTOL * scale, BETA_TOLERANCE * scale)
+            if metric_ok or beta_ok or beta == 1.0:
+                return beta, ess
+            if not use_metric:
+                if val < target:
+                    beta_max = beta
+                else:
+                    beta_min = beta
+            else:
+                if val < target:
+                    beta_min = beta
+                else:
+                    beta_max = beta
+        return beta, ess
+
+    def run(self) -> Optional[torch.Tensor]:
+        core = self.core
+        st = core.state
+        ens = core.ensemble
+        st.set_current("iter", st.raw("iter") + 1)
+        self.probe_log = []
+        n = self.n_particles
+        if ens.T == 0:                              # reweight.py:365-383
+            st.update_current({"beta": 0.0, "logz": 0.0, "ess": self.ess_ratio * n, "cv": 0.0})
+            return None                             # uniform 1/N weights, never consumed at beta = 0
+        beta_prev = float(st.raw("beta"))
+        target = self.ess_ratio * n
+        dynamic = self.volume_variation is not None
+        k = core.k
+        if not dynamic and self.device_search:
+            beta, ess, stats = self._device_search(beta_prev, target)
+        else:
+            lo, hi = self._ess_bracket(beta_prev, target)
+            if lo == hi:
+                beta = lo
+                ess, _ = self._probe(beta)
+            elif not dynamic:
+                beta, ess = self._bisect(beta_prev, hi, target, use_metric=False)
+            else:                                   # reweight.py:427-482
+                ess_prev, cv_prev = self._probe(beta_prev)
+                ess_high, cv_high = self._probe(hi)
+                need_probe = True
+                if self.volume_variation >= cv_high:
+                    beta, ess = hi, ess_high
+                elif self.volume_variation <= cv_prev:
+                    beta, ess = beta_prev, ess_prev
+                else:
+                    beta, ess = self._bisect(beta_prev, hi, self.volume_variation, use_metric=True)
+                    need_probe = False
+                if need_probe:
+                    ess, _ = self._probe(beta)
+            stats = k.probe_out                     # (m, S1, ..., logZ) of the last probe == probe(beta)
+        w = k.weights(ens, beta, stats, core.weights_buffer())
+        cv = k.volume_variation(ens.u, w, ens.n_total, ens.n_dim)     # reweight.py:417-419
+        logz = float(stats[4].item())
+        st.update_current({"logz": logz, "beta": float(beta), "ess": float(ess), "cv": cv})
+        return w
+
+    def _device_search(self, beta_prev: float, target: float):
+        """ESS mode: the whole bracket + bisection in one cooperative launch (tb_next_beta)."""
+        core = self.core
+        ens = core.ensemble
+        k = core.k
+        flags = 0
+        if core.warmup_regime:
+            # all stored generations are at beta = 0: every weight is exactly equal and the
+            # `ESS <= target` branch depends on numpy's rounding
+            ess0 = uniform_weights_ess(ens.n_total)
+            self.probe_log.append((beta_prev, ess0))
+            if ess0 <= target:
+                out = k.probe(ens, beta_prev)
+                return beta_prev, ess0, out
+            flags = 1
+        res, plog = k.next_beta(ens, beta_prev, target, flags)
+        h = res.cpu().numpy()
+        nprobe = int(h[6])
+        hp = plog[: 2 * min(nprobe, 512)].cpu().numpy().reshape(-1, 2)
+        self.probe_log.extend((float(b), float(e)) for b, e in hp)
+        if h[8] != 0.0:
+            raise FloatingPointError(f"{int(h[8])} non-finite log-weights in the persistent ensemble")
+        return float(h[0]), float(h[4]), res[1:7]     # (m, S1, S2, ESS, logZ, .) like tb_probe's out
+
+
+class Trainer:
+    """steps/train.py:65-127 (global, clustering=False branch) + modes.py:221-288 + student.py:6-116."""
+
+    def __init__(self, core):
+        self.core = core
+
+    def run(self, weights: Optional[torch.Tensor]) -> ModeStats:
+        core = self.core
+        ens = core.ensemble
+        d = ens.n_dim
+        if float(core.state.raw("beta")) == 0.0:      # train.py:79-88
+            return ModeStats.identity(d, core.device)
+        k = core.k
+        lib = k.lib
+        st = stream_ptr()
+        idx, wt = k.trim(weights, ens.n_total)
+        core.trace["trim_idx"], core.trace["trim_w"] = idx, wt
+        n_trim = int(idx.numel())
+        # modes.py:266-275: renormalise, draw 4n rows with replacement
+        stats3 = k.ws.f64("train_stats", 3)
+        _lib.check(lib.tb_normalize_inplace(ptr(wt), n_trim, ptr(k._reduce_ws), ptr(stats3), st), "normalize")
+        cdf = k.cdf(wt, n_trim, "train_cdf")
+        m_total = 4 * n_trim
+        draws = core.rng.train_u(m_total)
+        didx = k.ws.i64("train_didx", m_total)
+        k.search_right(cdf, n_trim, draws, didx)
+        counts = k.ws.i32("train_counts", n_trim)
+        _lib.check(lib.tb_count_indices(ptr(didx), m_total, ptr(counts), n_trim, st), "tb_count_indices")
+        core.trace["train_draw_idx"] = didx
+        # student.py:62: per-dimension median of the 4n-row multiset (even count: mean of the middle pair)
+        ranks = torch.tensor([m_total // 2 - 1, m_total // 2], dtype=torch.int64, device=core.device)
+        pair = k.ws.f64("train_pair", 2 * d)
+        sws = k.ws.bytes("select", lib.tb_select_workspace_bytes(d, 2))
+        _lib.check(lib.tb_select_ranks(ptr(ens.u), ptr(idx), d, n_trim, d, ptr(counts), ptr(ranks), 2, ptr(sws),
+                                       ptr(pair), st), "tb_select_ranks")
+        mean = torch.empty((1, d), dtype=F64, device=core.device)
+        _lib.check(lib.tb_median_pairs(ptr(pair), d, ptr(mean), st), "tb_median_pairs")
+        # student.py:63: Sigma = cov(ddof=1)*(M-1)/M + diag(var)/M from count-weighted moments
+        mws = k.ws.bytes("mom", lib.tb_moments_workspace_bytes(d))
+        cmean = k.ws.f64("train_cmean", d)
+        scatter = k.ws.f64("train_scatter", d * d)
+        _lib.check(lib.tb_counted_moments(ptr(ens.u), ptr(idx), ptr(counts), n_trim, d, 1.0 / m_total, ptr(mws),
+                                          ptr(cmean), ptr(scatter), st), "tb_counted_moments")
+        cov = torch.empty((1, d, d), dtype=F64, device=core.device)
+        _lib.check(lib.tb_student_sigma(ptr(scatter), d, float(m_total), ptr(cov), st), "tb_student_sigma")
+        # student.py:75-79 + modes.py:105-119: Cholesky (regularise on failure), inverse.  The EM loop
+        # returns on its first pass with nu = inf (student.py:54-55,93-94) -> dof = 1e6.
+        chol = torch.empty((1, d, d), dtype=F64, device=core.device)
+        inv = torch.empty((1, d, d), dtype=F64, device=core.device)
+        info = k.ws.i32("train_info", 1)
+        _lib.check(lib.tb_chol_inv(ptr(cov), d, 1, ptr(chol), ptr(inv), ptr(info), None, st), "tb_chol_inv")
+        dof = torch.full((1,), DOF_FALLBACK, dtype=F64, device=core.device)
+        return ModeStats(mean, cov, chol, inv, dof)
+
+
+class Resampler:
+    """steps/resample.py:52-99."""
+
+    def __init__(self, core):
+        self.core = core
+
+    def run(self, weights: Optional[torch.Tensor]) -> None:
+        core = self.core
+        st = core.state
+        n = core.config.n_particles
+        if float(st.raw("beta")) == 0.0:               # resample.py:69-72
+            st.set_current("assignments", np.zeros(n, dtype=int))
+            return
+        ens = core.ensemble
+        k = core.k
+        cdf = k.cdf(weights, ens.n_total)
+        idx = k.ws.i64("res_idx", n)
+        if core.config.resample == "mult":
+            k.search_right(cdf, ens.n_total, core.rng.resample_u(n), idx)
+        else:
+            k.systematic(cdf, ens.n_total, core.rng.resample_u0(), n, idx)
+        core.trace["resample_idx"] = idx
+        u = torch.empty((n, ens.n_dim), dtype=F64, device=core.device)
+        logl = torch.empty(n, dtype=F64, device=core.device)
+        _lib.check(k.lib.tb_gather_rows(ptr(ens.u), ptr(ens.logl), ens.n_dim, ptr(idx), n, ptr(u), ptr(logl),
+                                        stream_ptr()), "tb_gather_rows")
+        st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
+
+
+class Mutator:
+    """steps/mutate.py:76-200 + mcmc.py:142-323."""
+
+    CHUNK = 8   # Metropolis steps enqueued between looks at the device-side stop flag
+
+    def __init__(self, core):
+        self.core = core
+
+    def run(self, mode_stats: ModeStats) -> None:
+        core = self.core
+        st = core.state
+        cfg = core.config
+        n, d = cfg.n_particles, cfg.n_dim
+        k = core.k
+        lib = k.lib
+        sp = stream_ptr()
+        beta = float(st.raw("beta"))
+        params = core.mcmc_params(beta, mode_stats)
+        if beta == 0.0:                                # mutate.py:100-149
+            u = torch.empty((n, d), dtype=F64, device=core.device)
+            logl = torch.empty(n, dtype=F64, device=core.device)
+            tape_u = core.rng.prior_u(n, d)
+            _lib.check(lib.tb_prior_draw(n, C.byref(params), ptr(tape_u), ptr(u), None, ptr(logl), sp),
+                       "tb_prior_draw")
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int),
+                               "calls": st.raw("calls") + n, "steps": 1, "acceptance": 1.0, "efficiency": 1.0})
+            bad = torch.isinf(logl)
+            if bool(bad.any()):                         # mutate.py:122-148 (rare; bookkeeping on device tensors)
+                every = torch.arange(n, device=core.device)
+                inf_idx, fin_idx = every[bad], every[~bad]
+                if fin_idx.numel() > 0:
+                    pick = core.rng.inf_pick(fin_idx, int(inf_idx.numel()))
+                    u[inf_idx] = u[pick]
+                    logl[inf_idx] = logl[pick]
+                st.set_current("logz", st.raw("logz") + math.log(fin_idx.numel() / n))
+            return
+        u = st.raw("u")
+        logl = st.raw("logl")
+        K = mode_stats.K
+        ctrl = k.ws.f64("mcmc_ctrl", int(lib.tb_mcmc_ctrl_doubles(K)))
+        ws = k.ws.bytes("mcmc_ws", lib.tb_mcmc_workspace_bytes(n, K))
+        qcur = k.ws.f64("mcmc_q", n)
+        _lib.check(lib.tb_mcmc_begin(n, C.byref(params), None, ptr(u), ptr(qcur), ptr(ws), ptr(ctrl), sp),
+                   "tb_mcmc_begin")
+        tape = core.rng.mcmc_tape(n, d)
+        tape_ref = C.byref(tape) if tape is not None else None
+        n_min = cfg.n_steps * d
+        n_cap = cfg.n_max_steps * d
+        launched = 0
+        budget = min(n_min, n_cap)
+        while True:
+            if tape is not None:
+                budget = min(budget, tape.steps - launched)
+            if budget > 0:
+                _lib.check(lib.tb_mcmc_steps(n, C.byref(params), tape_ref, None, ptr(u), ptr(logl), ptr(qcur),
+                                             ptr(ws), ptr(ctrl), int(budget), sp), "tb_mcmc_steps")
+                launched += budget
+            h = ctrl.cpu().numpy()
+            if h[1] != 0.0 or launched >= n_cap:
+                break
+            if tape is not None and launched >= tape.steps:
+                raise RuntimeError(
+                    f"tape holds {tape.steps} MCMC steps but the device stop rule has not fired after {launched}")
+            budget = min(self.CHUNK, n_cap - launched)
+        core.n_mcmc_launches += launched
+        if h[4] != 0.0:
+            raise RuntimeError(f"MCMC kernel error flag {h[4]} (1: tape exhausted, 2: proposal never entered the cube)")
+        steps = int(h[0])
+        sig = h[8:8 + K]
+        sigma0 = 2.38 / math.sqrt(d)
+        core.trace["mcmc_sigma"] = sig.copy()
+        st.update_current({"u": u, "x": None, "logl": logl, "efficiency": float(np.mean(sig) / sigma0),
+                           "acceptance": float(h[3]), "steps": steps,
+                           "calls": st.raw("calls") + steps * core.n_global})

@@ -1,0 +1,351 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle / numpy on the same inputs.
+
+Bit-exact for indices, order statistics, cumulative sums and in-kernel likelihoods; 1e-10
+relative (north-star tolerance) for fp64 reductions whose summation order differs.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10  # BASELINE.json north_star: "within 1e-10 relative in fp64"
+
+
+@pytest.fixture(scope="module")
+def env():
+    from tempest_b200 import _lib
+    from tempest_b200.ensemble import PersistentEnsemble, ptr, stream_ptr
+    from tempest_b200.steps import Kernels
+
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+
+    class Env:
+        pass
+
+    e = Env()
+    e.lib, e.dev, e.ptr, e.sp, e.k = _lib.load(), dev, ptr, stream_ptr, Kernels(dev)
+    e.Ensemble = PersistentEnsemble
+    e._lib = _lib
+    return e
+
+
+def dev_arr(env, a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(env.dev)
+
+
+def synthetic_ensemble(env, n, T, d, seed=0, tau=1.0):
+    """SURVEY 8d synthetic persistent ensemble: logl ~ -0.5 chi2_d * tau, beta geometric after 3 zeros."""
+    from oracle import ps_oracle as po
+
+    rng = np.random.default_rng(seed)
+    betas = [0.0, 0.0, 0.0] + list(np.geomspace(1e-4, 1.0, max(T - 3, 1)))[: max(T - 3, 0)]
+    betas = betas[:T]
+    ens = env.Ensemble(d, env.dev)
+    gens_l, gens_u, logzs = [], [], []
+    for t in range(T):
+        u = rng.random((n, d))
+        logl = -0.5 * tau * rng.chisquare(d, n) * (1.0 + 3.0 * rng.random(n))
+        logz = 0.0 if t == 0 else po.log_weights_and_logz(gens_l, betas[:t], logzs, betas[t])[1]
+        ens.append(dev_arr(env, u), dev_arr(env, logl), betas[t], logz)
+        gens_l.append(logl)
+        gens_u.append(u)
+        logzs.append(logz)
+    return ens, gens_l, gens_u, betas, logzs
+
+
+# ---------------------------------------------------------------------------------------
+def test_mixture_probe_weights_match_oracle(env):
+    from oracle import ps_oracle as po
+
+    for (n, T, d) in [(64, 5, 3), (1000, 9, 10), (4096, 24, 10)]:
+        ens, gl, gu, betas, logzs = synthetic_ensemble(env, n, T, d, seed=n)
+        c_inc = ens.C[: ens.n_total].clone()
+        ens.rebuild_mixture()
+        assert torch.equal(c_inc, ens.C[: ens.n_total]), "incremental log-mixture != full rebuild"
+        for beta in (0.0, betas[-1], 0.37, 1.0):
+            logw_ref, logz_ref = po.log_weights_and_logz(gl, betas, logzs, beta)
+            w_ref = np.exp(logw_ref - logw_ref.max())
+            ess_ref = po.effective_sample_size(w_ref)
+            out = env.k.probe(ens, beta).cpu().numpy()
+            assert out[5] == 0
+            assert out[3] == pytest.approx(ess_ref, rel=RTOL)
+            assert out[4] == pytest.approx(logz_ref, rel=RTOL, abs=1e-12)
+            w = torch.empty(ens.n_total, dtype=torch.float64, device=env.dev)
+            env.k.weights(ens, beta, env.k.probe_out, w)
+            np.testing.assert_allclose(w.cpu().numpy(), w_ref / w_ref.sum(), rtol=RTOL, atol=1e-300)
+            env.k.weights(ens, beta, env.k.probe_out, w, log=True)
+            np.testing.assert_allclose(w.cpu().numpy(), logw_ref, rtol=RTOL, atol=1e-9)
+
+
+def test_next_beta_device_search_matches_oracle_probe_sequence(env):
+    from oracle import ps_oracle as po
+
+    for (n, T, d, seed) in [(256, 6, 4, 1), (1024, 12, 10, 2), (5000, 20, 10, 3)]:
+        ens, gl, gu, betas, logzs = synthetic_ensemble(env, n, T, d, seed=seed)
+        beta_prev = betas[-1] * 0.5
+        target = 2.0 * n
+
+        def probe(b):
+            lw, _ = po.log_weights_and_logz(gl, betas, logzs, b)
+            w = np.exp(lw - lw.max())
+            return w, po.effective_sample_size(w), 0.0
+
+        s = po.BetaSearch(probe, False)
+        lo, hi = s.ess_bracket(beta_prev, target)
+        if lo == hi:
+            beta_ref = lo
+            _, ess_ref, _ = s.probe(lo)
+        else:
+            beta_ref, _, ess_ref = s.bisect(beta_prev, hi, target, False)
+        res, plog = env.k.next_beta(ens, beta_prev, target, 0)
+        h = res.cpu().numpy()
+        nprobe = int(h[6])
+        got = plog[: 2 * nprobe].cpu().numpy().reshape(-1, 2)
+        # the oracle re-probes beta when lo == hi; the device reuses the probe it already has
+        ref_log = np.array(s.log if lo != hi else s.log[:-1])
+        assert h[0] == beta_ref                                    # bit-exact beta
+        np.testing.assert_array_equal(got[:, 0], ref_log[:, 0])    # identical probe sequence
+        np.testing.assert_allclose(got[:, 1], ref_log[:, 1], rtol=RTOL)
+        assert h[4] == pytest.approx(ess_ref, rel=RTOL)
+        # the one-launch search equals the host-driven search kernel by kernel
+        out = env.k.probe(ens, h[0]).cpu().numpy()
+        np.testing.assert_array_equal(out[:5], h[1:6])
+
+
+@pytest.mark.parametrize("kind", ["uniform", "skewed", "tiny", "zeros", "ascending", "equal", "spiky"])
+@pytest.mark.parametrize("n", [1, 2, 31, 512, 513, 4097, 100003, 1 << 20])
+def test_cdf_exact_is_bitwise_numpy_cumsum(env, kind, n):
+    rng = np.random.default_rng(hash((kind, n)) % (2**32))
+    if kind == "uniform":
+        p = rng.random(n)
+    elif kind == "skewed":
+        p = np.exp(-0.5 * rng.chisquare(10, n) * 40.0)
+    elif kind == "tiny":
+        p = rng.random(n) * 1e-300
+    elif kind == "zeros":
+        p = rng.random(n) * (rng.random(n) < 0.3)
+        p[: min(n, 5)] = 0.0
+    elif kind == "ascending":
+        p = np.sort(np.exp(rng.normal(size=n) * 30.0))
+    elif kind == "equal":
+        p = np.full(n, 1.0 / n)
+    else:
+        p = rng.random(n) * 1e-12
+        p[rng.integers(0, n, size=max(1, n // 1000))] = 1.0
+    if p.sum() > 0:
+        p = p / p.sum()
+    ref = np.cumsum(p)
+    dp = dev_arr(env, p)
+    out = env.k.cdf(dp, n, "t_cdf")
+    got = out.cpu().numpy()
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), \
+        f"first mismatch at {np.nonzero(got != ref)[0][:3]}"
+
+
+def test_cdf_sequential_kernel_agrees(env):
+    rng = np.random.default_rng(9)
+    n = 50000
+    p = rng.random(n) ** 3
+    p /= p.sum()
+    dp = dev_arr(env, p)
+    out = torch.empty(n, dtype=torch.float64, device=env.dev)
+    env._lib.check(env.lib.tb_cdf_sequential(env.ptr(dp), n, env.ptr(out), env.sp()))
+    assert np.array_equal(out.cpu().numpy(), np.cumsum(p))
+
+
+def test_multinomial_and_systematic_indices_bit_exact(env):
+    from oracle import ps_oracle as po
+
+    rng = np.random.default_rng(4)
+    for n, m in [(100, 64), (5000, 4096), (1 << 18, 1 << 16)]:
+        p = np.exp(-0.5 * rng.chisquare(6, n) * 5.0)
+        p /= p.sum()
+        u = rng.random(m)
+        ref = po.legacy_choice_indices(p, u)
+        dp = dev_arr(env, p)
+        cdf = env.k.cdf(dp, n, "t_cdf")
+        idx = torch.empty(m, dtype=torch.int64, device=env.dev)
+        env.k.search_right(cdf, n, dev_arr(env, u), idx)
+        np.testing.assert_array_equal(idx.cpu().numpy(), ref)
+        u0 = float(rng.random())
+        ref_s = po.systematic_indices(m, p, u0)
+        env.k.systematic(cdf, n, u0, m, idx)
+        np.testing.assert_array_equal(idx.cpu().numpy(), ref_s)
+    # edge: draw exactly on a boundary / at 0
+    p = np.array([0.25, 0.25, 0.5])
+    cdf = env.k.cdf(dev_arr(env, p), 3, "t_cdf")
+    u = np.array([0.0, 0.25, 0.5, 0.4999999999999999, 0.9999999999999999])
+    idx = torch.empty(5, dtype=torch.int64, device=env.dev)
+    env.k.search_right(cdf, 3, dev_arr(env, u), idx)
+    np.testing.assert_array_equal(idx.cpu().numpy(), po.legacy_choice_indices(p, u))
+
+
+def test_gather_rows(env):
+    rng = np.random.default_rng(5)
+    n, d, m = 1000, 10, 333
+    u = rng.random((n, d))
+    l = rng.normal(size=n)
+    idx = rng.integers(0, n, m)
+    au = torch.empty((m, d), dtype=torch.float64, device=env.dev)
+    al = torch.empty(m, dtype=torch.float64, device=env.dev)
+    env._lib.check(env.lib.tb_gather_rows(env.ptr(dev_arr(env, u)), env.ptr(dev_arr(env, l)), d,
+                                          env.ptr(dev_arr(env, idx)), m, env.ptr(au), env.ptr(al), env.sp()))
+    np.testing.assert_array_equal(au.cpu().numpy(), u[idx])
+    np.testing.assert_array_equal(al.cpu().numpy(), l[idx])
+
+
+@pytest.mark.parametrize("d", [1, 2, 7, 10, 16, 50, 100])
+def test_volume_variation_matches_oracle(env, d):
+    from oracle import ps_oracle as po
+
+    rng = np.random.default_rng(d)
+    n = 4000 if d <= 16 else 1500
+    u = rng.random((n, d))
+    w = np.exp(-0.5 * rng.chisquare(4, n))
+    w /= w.sum()
+    got = env.k.volume_variation(dev_arr(env, u), dev_arr(env, w), n, d)
+    assert got == pytest.approx(po.volume_variation(u, w), rel=1e-9)
+    # too few samples -> 1e10 (tools.py:87-88)
+    assert env.k.volume_variation(dev_arr(env, u[:d]), dev_arr(env, w[:d]), d, d) == 1e10
+
+
+def test_volume_variation_rank_deficient_regularises(env):
+    from oracle import ps_oracle as po
+
+    rng = np.random.default_rng(1)
+    n, d = 500, 4
+    u = rng.random((n, d))
+    u[:, 3] = u[:, 0]                       # exactly collinear -> matrix_rank < d
+    w = np.full(n, 1.0 / n)
+    got = env.k.volume_variation(dev_arr(env, u), dev_arr(env, w), n, d)
+    assert got == pytest.approx(po.volume_variation(u, w), rel=1e-6)
+
+
+@pytest.mark.parametrize("n,kind", [(40, "flat"), (1000, "skewed"), (20000, "skewed"), (300000, "heavy"),
+                                    (4096, "equal"), (5000, "dups")])
+def test_trim_matches_oracle(env, n, kind):
+    from oracle import ps_oracle as po
+
+    rng = np.random.default_rng(n)
+    if kind == "flat":
+        w = 1.0 + 0.1 * rng.random(n)
+    elif kind == "skewed":
+        w = np.exp(-0.5 * rng.chisquare(10, n))
+    elif kind == "heavy":
+        w = np.exp(-0.5 * rng.chisquare(10, n) * 8.0)
+    elif kind == "equal":
+        w = np.ones(n)
+    else:
+        w = np.repeat(np.exp(-rng.chisquare(3, n // 10)), 10)
+    w_ref = w.copy()
+    idx_ref, wt_ref, i_ref = po.trim_weights(w_ref)
+    dw = dev_arr(env, w)
+    idx, wt = env.k.trim(dw, n)
+    assert env.k.last_trim["bin"] == i_ref
+    np.testing.assert_array_equal(idx.cpu().numpy(), idx_ref)
+    np.testing.assert_allclose(wt.cpu().numpy(), wt_ref, rtol=RTOL)
+    np.testing.assert_allclose(dw.cpu().numpy(), w_ref, rtol=RTOL)   # normalised in place (tools.py:36)
+
+
+def test_select_ranks_exact(env):
+    rng = np.random.default_rng(6)
+    n, d = 3001, 5
+    u = rng.random((n, d))
+    u[::7] = u[3]                                    # ties
+    rows = rng.permutation(n)[:2000].astype(np.int64)
+    mult = rng.integers(0, 5, size=2000).astype(np.int32)
+    m_total = int(mult.sum())
+    ranks = np.array([m_total // 2 - 1, m_total // 2], dtype=np.int64)
+    out = torch.empty(2 * d, dtype=torch.float64, device=env.dev)
+    ws = torch.zeros(env.lib.tb_select_workspace_bytes(d, 2), dtype=torch.uint8, device=env.dev)
+    env._lib.check(env.lib.tb_select_ranks(env.ptr(dev_arr(env, u)), env.ptr(dev_arr(env, rows)), d, 2000, d,
+                                           env.ptr(dev_arr(env, mult)), env.ptr(dev_arr(env, ranks)), 2,
+                                           env.ptr(ws), env.ptr(out), env.sp()))
+    expanded = np.repeat(u[rows], mult, axis=0)
+    srt = np.sort(expanded, axis=0)
+    np.testing.assert_array_equal(out.cpu().numpy().reshape(d, 2), srt[ranks].T)
+
+
+@pytest.mark.parametrize("d", [1, 3, 10, 50, 100])
+def test_chol_inv_and_regularisation(env, d):
+    rng = np.random.default_rng(d)
+    a = rng.normal(size=(d, d))
+    spd = a @ a.T / d + 0.1 * np.eye(d)
+    bad = spd.copy()
+    bad[:, -1] = bad[:, 0]
+    bad[-1, :] = bad[0, :]                           # singular -> regularised (modes.py:114-119)
+    mats = np.stack([spd, bad]) if d > 1 else np.stack([spd, np.zeros((1, 1))])
+    dm = dev_arr(env, mats)
+    chol = torch.empty_like(dm)
+    inv = torch.empty_like(dm)
+    info = torch.zeros(2, dtype=torch.int32, device=env.dev)
+    env._lib.check(env.lib.tb_chol_inv(env.ptr(dm), d, 2, env.ptr(chol), env.ptr(inv), env.ptr(info), None, env.sp()))
+    assert info.cpu().tolist() == [0, 1]
+    np.testing.assert_allclose(chol[0].cpu().numpy(), np.linalg.cholesky(spd), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(inv[0].cpu().numpy(), np.linalg.inv(spd), rtol=1e-8, atol=1e-10)
+    reg = mats[1] + np.eye(d) * max(1e-6, 1e-6 * abs(np.trace(mats[1])))
+    np.testing.assert_allclose(dm[1].cpu().numpy(), reg, rtol=1e-14)
+    np.testing.assert_allclose(chol[1].cpu().numpy(), np.linalg.cholesky(reg), rtol=1e-6, atol=1e-9)
+
+
+def _params(env, prior, like, d, rng_mode=0, seed=7, iteration=1, **kw):
+    p = env._lib.TbMcmcParams()
+    p.n_dim, p.n_modes, p.sampler, p.rng_mode = d, 1, 0, rng_mode
+    p.like_id, p.prior_id, p.n_steps, p.n_max = like.kernel_id, prior.kernel_id, 1, 20
+    p.beta, p.seed, p.iteration, p.slot_offset, p.n_global = 0.0, seed, iteration, 0, 0
+    keep = [dev_arr(env, like.dparams()), dev_arr(env, prior.dparams())]
+    p.like_params, p.prior_params = keep[0].data_ptr(), keep[1].data_ptr()
+    return p, keep
+
+
+def test_prior_draw_and_likelihoods_bit_exact(env):
+    from tempest_b200 import registry as reg
+
+    rng = np.random.default_rng(8)
+    cases = [
+        (reg.UniformPrior(-10, 10, 10), reg.Rosenbrock(10)),
+        (reg.UniformPrior(-10, 10, 50), reg.GaussianLikelihood.ar1(50)),
+        (reg.UniformPrior(-10, 10, 2), reg.IsotropicMixture.four_corners(2)),
+        (reg.UniformPrior(-6, 6, 100), reg.TwinShells(100)),
+        (reg.UniformPrior(-6, 6, 4), reg.TwinShells(4)),
+    ]
+    for prior, like in cases:
+        d, n = prior.n_dim, 777
+        tape_u = rng.random((n, d))
+        p, keep = _params(env, prior, like, d, rng_mode=1)
+        u = torch.empty((n, d), dtype=torch.float64, device=env.dev)
+        x = torch.empty((n, d), dtype=torch.float64, device=env.dev)
+        logl = torch.empty(n, dtype=torch.float64, device=env.dev)
+        env._lib.check(env.lib.tb_prior_draw(n, C.byref(p), env.ptr(dev_arr(env, tape_u)), env.ptr(u), env.ptr(x),
+                                             env.ptr(logl), env.sp()))
+        np.testing.assert_array_equal(u.cpu().numpy(), tape_u)
+        x_ref = np.array([prior(r) for r in tape_u])
+        np.testing.assert_array_equal(x.cpu().numpy(), x_ref)
+        ref = like(x_ref)
+        got = logl.cpu().numpy()
+        if like.kernel_id in (reg.LIKE_ROSENBROCK, reg.LIKE_GAUSSIAN):
+            np.testing.assert_array_equal(got, ref)               # only + - * : bit-exact
+        else:
+            np.testing.assert_allclose(got, ref, rtol=1e-13)       # exp/log/sqrt differ by ulps
+
+
+def test_philox_uniforms_are_reproducible_and_uniform(env):
+    n = 1 << 16
+    a = torch.empty(n, dtype=torch.float64, device=env.dev)
+    b = torch.empty(n, dtype=torch.float64, device=env.dev)
+    env._lib.check(env.lib.tb_philox_uniform(123, 5, 4, 0, n, env.ptr(a), env.sp()))
+    env._lib.check(env.lib.tb_philox_uniform(123, 5, 4, 0, n, env.ptr(b), env.sp()))
+    assert torch.equal(a, b)
+    env._lib.check(env.lib.tb_philox_uniform(123, 6, 4, 0, n, env.ptr(b), env.sp()))
+    assert not torch.equal(a, b)
+    h = a.cpu().numpy()
+    assert 0.0 <= h.min() and h.max() < 1.0
+    assert abs(h.mean() - 0.5) < 0.01 and abs(h.var() - 1 / 12) < 0.005
+    # sharding invariance: offset selects a window of the same stream
+    env._lib.check(env.lib.tb_philox_uniform(123, 5, 4, 1000, 100, env.ptr(b), env.sp()))
+    assert torch.equal(a[1000:1100], b[:100])

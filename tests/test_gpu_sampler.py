@@ -1,0 +1,181 @@
+"""End-to-end parity of the device sampler with the CPU oracle (and, through the committed
+golden fixtures, with the unmodified reference) on shared random-variate tapes.
+
+The oracle is run on numpy's legacy MT19937 stream (the reference's own stream), records every
+variate it consumes per PS iteration, and the CUDA path replays those tapes.  Discrete outputs
+(beta sequence, trim set, training draws, resampling indices, MCMC step counts, accept
+decisions) must be identical; continuous outputs must agree to 1e-10 relative (north star).
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN  # noqa: E402
+
+RTOL = 1e-10
+
+
+def run_pair(name, max_iterations=None):
+    """Oracle on LegacyStream(seed) with recording, then the device sampler on its tapes."""
+    import tempest_b200 as tp
+    from oracle import ps_oracle as po
+    from oracle.gen_golden import cases
+    from tempest_b200.rng import TapeSource
+
+    prior, like, kw, n_total, seed = cases()[name]
+    okw = {k: v for k, v in kw.items() if k != "clustering"}
+    o = po.OraclePS(prior, like, stream=po.LegacyStream(seed), record=True, **okw)
+    o.run(n_total, max_iterations=max_iterations)
+    s = tp.Sampler(prior, like, vectorize=True, **kw)
+    core = s._core
+    core.rng = TapeSource(o.tapes, core.device)
+    core._initialize_fresh()
+    core.n_total = int(n_total)
+    traces = []
+    k = 0
+    while core._not_termination():
+        core.execute_iteration()
+        tr = {key: (v.cpu().numpy() if hasattr(v, "cpu") else v) for key, v in core.trace.items()}
+        tr["probe_log"] = list(core.reweighter.probe_log)
+        tr["mode_mean"] = core.last_mode_stats.means.cpu().numpy()
+        tr["mode_cov"] = core.last_mode_stats.covariances.cpu().numpy()
+        traces.append(tr)
+        k += 1
+        if max_iterations is not None and k >= max_iterations:
+            break
+    core.state.set_current("logz", float(core._last_posterior_probe[4]))
+    return o, s, traces
+
+
+@pytest.mark.parametrize("name", ["rosen10_n64_tpcn_mult", "gauss4_n32_rwm_syst_bc", "mix2_n21_tpcn_mult",
+                                  "shell4_n48_dynamic"])
+def test_full_run_matches_oracle_on_tapes(name):
+    o, s, traces = run_pair(name)
+    st = s.state
+    T = len(o.hist["beta"])
+    assert st.get_history_length() == T
+    # discrete: beta sequence, step counts, call counts
+    np.testing.assert_array_equal(st.get_history("beta"), np.array(o.hist["beta"]))
+    np.testing.assert_array_equal(st.get_history("steps"), np.array(o.hist["steps"]))
+    np.testing.assert_array_equal(st.get_history("calls"), np.array(o.hist["calls"]))
+    np.testing.assert_array_equal(st.get_history("iter"), np.array(o.hist["iter"]))
+    for t, (tr, otr) in enumerate(zip(traces, o.traces)):
+        for key in ("trim_idx", "train_draw_idx", "resample_idx"):
+            if key in otr:
+                np.testing.assert_array_equal(tr[key], otr[key], err_msg=f"{key} @ iteration {t}")
+        # probe sequence (the oracle re-probes the final beta when the bracket collapses)
+        mine = np.array(tr["probe_log"]).reshape(-1, 2)
+        ref = np.array(otr["probes"]).reshape(-1, 2)
+        if len(ref) == len(mine) + 1:
+            ref = ref[:-1]
+        np.testing.assert_array_equal(mine[:, 0], ref[:, 0], err_msg=f"probe betas @ iteration {t}")
+        np.testing.assert_allclose(mine[:, 1], ref[:, 1], rtol=RTOL)
+        if "mode_mean" in otr:
+            np.testing.assert_array_equal(tr["mode_mean"], otr["mode_mean"])      # medians: exact
+            np.testing.assert_allclose(tr["mode_cov"], otr["mode_cov"], rtol=1e-9, atol=1e-14)
+    # continuous: every generation of particles, evidence, ESS, cv, acceptance
+    np.testing.assert_allclose(st.get_history("logz"), np.array(o.hist["logz"]), rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(st.get_history("ess"), np.array(o.hist["ess"]), rtol=RTOL)
+    np.testing.assert_allclose(st.get_history("cv"), np.array(o.hist["cv"]), rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(st.get_history("acceptance"), np.array(o.hist["acceptance"]), rtol=RTOL)
+    np.testing.assert_allclose(st.get_history("efficiency"), np.array(o.hist["efficiency"]), rtol=RTOL)
+    np.testing.assert_allclose(st.get_history("u"), np.array(o.hist["u"]), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(st.get_history("x"), np.array(o.hist["x"]), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(st.get_history("logl"), np.array(o.hist["logl"]), rtol=1e-9, atol=1e-9)
+    # accept/reject decisions: a flipped decision would leave a walker at a different point
+    du = np.abs(st.get_history("u") - np.array(o.hist["u"])).max()
+    assert du < 1e-12, f"walker positions differ by {du}: an accept/reject decision flipped"
+    assert s.evidence()[0] == pytest.approx(o.evidence()[0], rel=RTOL)
+    # posterior() against the oracle and against the reference's own output (golden fixture)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x, w, l, logw = s.posterior(return_logw=True)
+    assert x.shape == g["post_x"].shape
+    np.testing.assert_allclose(x, g["post_x"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(w, g["post_w"], rtol=1e-9)
+    np.testing.assert_allclose(l, g["post_logl"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(logw, g["post_logw"], rtol=1e-9, atol=1e-9)
+    assert s.evidence()[0] == pytest.approx(float(g["final_logz"]), rel=RTOL)
+    np.testing.assert_array_equal(st.get_history("beta"), g["h_beta"])
+    np.testing.assert_array_equal(st.get_history("steps"), g["h_steps"])
+
+
+def test_host_driven_search_equals_device_search():
+    import tempest_b200 as tp
+
+    outs = []
+    for device_search in (True, False):
+        s = tp.Sampler(tp.UniformPrior(-10, 10, 10), tp.Rosenbrock(10), 10, n_particles=512, vectorize=True,
+                       clustering=False, random_state=5)
+        s._core.reweighter.device_search = device_search
+        s._core._initialize_fresh()
+        for _ in range(8):
+            s.sample()
+        outs.append((s.state.get_history("beta"), s.state.get_history("logz"), s.state.get_history("logl")))
+    for a, b in zip(*outs):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_philox_run_is_reproducible_and_recovers_gaussian_evidence():
+    # reference tests/test_end_to_end.py: 10-D diagonal Gaussian, U(-10,10) prior, logZ = -29.96 +- 0.5
+    import tempest_b200 as tp
+
+    mean = np.array([2.0, -1.5, 0.5, 3.2, -2.8, 1.1, -0.7, 2.5, -1.2, 0.9])
+    var = np.array([1.0, 0.8, 1.2, 0.9, 1.1, 0.7, 1.3, 0.85, 1.15, 0.95])
+
+    def run():
+        s = tp.Sampler(tp.UniformPrior(-10, 10, 10), tp.GaussianLikelihood(mean, var), 10, n_particles=1024,
+                       vectorize=True, clustering=False, random_state=42, n_steps=1)
+        s.run(n_total=4096, progress=False)
+        return s
+
+    s = run()
+    logz, err = s.evidence()
+    assert err is None and abs(logz - (-29.96)) < 0.5
+    x, w, l = s.posterior()
+    assert x.shape[1] == 10 and x.shape[0] == w.shape[0] == l.shape[0]
+    assert w.sum() == pytest.approx(1.0, abs=1e-12)
+    pm = np.average(x, weights=w, axis=0)
+    np.testing.assert_allclose(pm, mean, atol=0.25)
+    pc = np.cov(x, rowvar=False, aweights=w)
+    np.testing.assert_allclose(np.diag(pc), var, atol=0.5)
+    assert s.beta > 0.99 and s.state.get_current("acceptance") > 0.1
+    s2 = run()
+    np.testing.assert_array_equal(s2.state.get_history("beta"), s.state.get_history("beta"))
+    np.testing.assert_array_equal(s2.state.get_history("logl", flat=True), s.state.get_history("logl", flat=True))
+    assert s2.evidence()[0] == logz
+    # resampled posterior has uniform weights (core.py:222-231)
+    xr, wr, lr = s.posterior(resample=True)
+    assert np.all(wr == 1.0 / len(wr))
+
+
+def test_sample_contract_and_state_surface():
+    # reference tests/test_sample_method.py:80-146, tests/test_state_manager.py:204-281
+    import tempest_b200 as tp
+    from tempest_b200.ensemble import CURRENT_STATE_KEYS
+
+    s = tp.Sampler(tp.UniformPrior(-10, 10, 4), tp.Rosenbrock(4), 4, n_particles=32, vectorize=True,
+                   clustering=False, random_state=1)
+    logw, logz = s.state.compute_logw_and_logz(1.0)
+    assert logw.size == 0 and logz == -np.inf
+    out = s.sample()
+    assert set(out) == set(CURRENT_STATE_KEYS)
+    assert out["u"].shape == (32, 4) and out["x"].shape == (32, 4) and out["logl"].shape == (32,)
+    assert out["beta"] == 0.0 and out["ess"] == 64.0 and out["iter"] == 1 and out["calls"] == 32
+    out["u"][:] = -1.0                                       # copies, not views
+    assert s.state.get_current("u").min() >= 0.0
+    for _ in range(4):
+        s.sample()
+    assert s.state.get_history_length() == 5
+    assert s.state.get_history("u").shape == (5, 32, 4)
+    assert s.state.get_history("logl", flat=True).shape == (160,)
+    logw, logz = s.state.compute_logw_and_logz(1.0)
+    assert np.exp(logw).sum() == pytest.approx(1.0, abs=1e-9) and np.isfinite(logz)
+    assert s.n_dim == 4 and s.n_particles == 32 and s.resample == "mult" and s.clustering is False
+    with pytest.raises(NotImplementedError):
+        tp.Sampler(tp.UniformPrior(-1, 1, 2), lambda x: -np.sum(x * x, axis=1), 2, vectorize=True, clustering=False)
+    with pytest.raises(ValueError, match="Invalid resample"):
+        tp.Sampler(tp.UniformPrior(-1, 1, 2), tp.Rosenbrock(2), 2, vectorize=True, clustering=False, resample="x")

@@ -1,0 +1,105 @@
+"""CPU-only checks: host-side scalar logic, configuration, and that the C-ABI library loads and
+exports every symbol include/tempest_b200.h declares (no compute calls without a GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from tempest_b200 import _lib, build
+
+    build.build(verbose=False)
+    lib = _lib.load_library()
+    header = open(os.path.join(ROOT, "include", "tempest_b200.h")).read()
+    declared = set(re.findall(r"\b(tb_[a-z0-9_]+)\s*\(", header)) - {"tb_stream_t"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) <= declared
+    assert lib.tb_version() == 100
+
+
+def test_uniform_weights_ess_matches_numpy():
+    from tempest_b200.steps import uniform_weights_ess, numpy_pairwise_sum_equal
+
+    for n in list(range(1, 300)) + [1000, 1023, 1024, 3000, 4097, 12345, 65536, 3 * 21, 1 << 20]:
+        w = np.ones(n)
+        w = w / np.sum(w)
+        assert uniform_weights_ess(n) == 1.0 / np.sum(w**2.0), n
+    for n in (5, 77, 129, 5000):
+        assert numpy_pairwise_sum_equal(0.1, n) == float(np.sum(np.full(n, 0.1)))
+
+
+def test_percentile_restatement_matches_numpy():
+    from tempest_b200.steps import numpy_lerp, percentile_position
+
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 10, 101, 1000, 4099):
+        w = rng.random(n) ** 5
+        s = np.sort(w)
+        for p in np.linspace(0, 99, 1000)[:: max(1, 1000 // 97)]:
+            lo, hi, g = percentile_position(n, float(p))
+            assert numpy_lerp(s[lo], s[hi], g) == np.percentile(w, p), (n, p)
+
+
+def test_config_defaults_and_validation():
+    from tempest_b200.config import SamplerConfig
+
+    f = lambda x: x  # noqa: E731
+    c = SamplerConfig(prior_transform=f, log_likelihood=f, n_dim=3)
+    assert (c.n_particles, c.n_steps, c.n_max_steps, c.resample, c.sample) == (6, 1, 20, "mult", "tpcn")
+    assert str(c.output_dir) == "states" and c.output_label == "ps"
+    with pytest.raises(ValueError, match="Invalid sampler 'hmc'"):
+        SamplerConfig(prior_transform=f, log_likelihood=f, n_dim=3, sample="hmc")
+    with pytest.raises(ValueError, match="Cannot vectorize likelihood with blobs"):
+        SamplerConfig(prior_transform=f, log_likelihood=f, n_dim=3, vectorize=True, blobs_dtype="f8")
+    with pytest.raises(ValueError, match="both periodic and reflective"):
+        SamplerConfig(prior_transform=f, log_likelihood=f, n_dim=3, periodic=[0], reflective=[0])
+    with pytest.raises(ValueError, match="n_dim must be int"):
+        SamplerConfig(prior_transform=f, log_likelihood=f, n_dim=2.5)
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    import tempest_b200 as tp
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        tp.Sampler(tp.UniformPrior(-1, 1, 2), tp.Rosenbrock(2), 2, vectorize=True, clustering=False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "tempest_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), fn
+
+
+def test_registry_matches_readme_rosenbrock():
+    from tempest_b200.registry import Rosenbrock, UniformPrior
+
+    rng = np.random.default_rng(3)
+    x = UniformPrior(-10, 10, 10)(rng.random((257, 10)))
+    readme = -np.sum(10.0 * (x[:, ::2] ** 2.0 - x[:, 1::2]) ** 2.0 + (x[:, ::2] - 1.0) ** 2.0, axis=1)
+    np.testing.assert_array_equal(Rosenbrock(10)(x), readme)
+    np.testing.assert_array_equal(UniformPrior(-10, 10, 10)(np.full(10, 0.25)), 20 * np.full(10, 0.25) - 10)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    from oracle.philox import philox4x32
+
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+           ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+            (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
+    for ctr, key, want in kat:
+        got = philox4x32(*ctr, *key)
+        assert tuple(int(v) for v in got) == want
