@@ -144,19 +144,46 @@ class SamplerCore:
         self._last_posterior_probe = h
         return 1.0 - float(self.state.raw("beta")) >= 1e-4 or h[3] < self.n_total
 
-    def execute_iteration(self, save_every=None, t0: int = 0) -> dict:
+    def _stage(self, name: str):
+        """CUDA-event stage timer (enabled by ``self.profile = True``; bench.py reads ``stage_ms``)."""
+        if not getattr(self, "profile", False):
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._stage_events.append((name, ev))
+
+    def _flush_stages(self) -> None:
+        if not getattr(self, "profile", False) or len(self._stage_events) < 2:
+            return
+        torch.cuda.synchronize()
+        for (name, a), (_, b) in zip(self._stage_events[:-1], self._stage_events[1:]):
+            self.stage_ms[name] = self.stage_ms.get(name, 0.0) + a.elapsed_time(b)
+        self._stage_events = []
+
+    def execute_iteration(self, save_every=None, t0: int = 0, export: bool = True) -> dict:
         self.trace = {}
+        if getattr(self, "profile", False):
+            self._stage_events = []
+            if not hasattr(self, "stage_ms"):
+                self.stage_ms = {}
         self.rng.begin_iteration(int(self.state.raw("iter") or 0) + 1)
+        self._stage("reweight")
         weights = self.reweighter.run()
+        self._stage("train")
         mode_stats = self.trainer.run(weights)
+        self._stage("resample")
         self.resampler.run(weights)
+        self._stage("mutate")
         self.mutator.run(mode_stats)
+        self._stage("commit")
         # commit (state_manager.py:356-416): particles to the device ensemble, scalars to host lists
         st = self.state
         self.ensemble.append(st.raw("u"), st.raw("logl"), float(st.raw("beta")), float(st.raw("logz")))
         st.commit_scalars()
+        self._stage("end")
+        self._flush_stages()
         self.last_mode_stats = mode_stats
-        return st.get_current()
+        return st.get_current() if export else None
 
     def run_sampling(self, n_total: int = 4096, progress: bool = True, resume_state_path=None,
                      save_every: Optional[int] = None) -> None:
@@ -170,7 +197,7 @@ class SamplerCore:
 
             pbar = tqdm(desc="Iter")
         while self._not_termination():
-            self.execute_iteration()
+            self.execute_iteration(export=False)
             if pbar is not None:
                 st = self.state
                 pbar.update(1)

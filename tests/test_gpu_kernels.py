@@ -170,7 +170,8 @@ def test_multinomial_and_systematic_indices_bit_exact(env):
         dp = dev_arr(env, p)
         cdf = env.k.cdf(dp, n, "t_cdf")
         idx = torch.empty(m, dtype=torch.int64, device=env.dev)
-        env.k.search_right(cdf, n, dev_arr(env, u), idx)
+        du = dev_arr(env, u)
+        env.k.search_right(cdf, n, du, idx)
         np.testing.assert_array_equal(idx.cpu().numpy(), ref)
         u0 = float(rng.random())
         ref_s = po.systematic_indices(m, p, u0)
@@ -181,7 +182,8 @@ def test_multinomial_and_systematic_indices_bit_exact(env):
     cdf = env.k.cdf(dev_arr(env, p), 3, "t_cdf")
     u = np.array([0.0, 0.25, 0.5, 0.4999999999999999, 0.9999999999999999])
     idx = torch.empty(5, dtype=torch.int64, device=env.dev)
-    env.k.search_right(cdf, 3, dev_arr(env, u), idx)
+    du = dev_arr(env, u)
+    env.k.search_right(cdf, 3, du, idx)
     np.testing.assert_array_equal(idx.cpu().numpy(), po.legacy_choice_indices(p, u))
 
 
@@ -193,8 +195,9 @@ def test_gather_rows(env):
     idx = rng.integers(0, n, m)
     au = torch.empty((m, d), dtype=torch.float64, device=env.dev)
     al = torch.empty(m, dtype=torch.float64, device=env.dev)
-    env._lib.check(env.lib.tb_gather_rows(env.ptr(dev_arr(env, u)), env.ptr(dev_arr(env, l)), d,
-                                          env.ptr(dev_arr(env, idx)), m, env.ptr(au), env.ptr(al), env.sp()))
+    du, dl, di = dev_arr(env, u), dev_arr(env, l), dev_arr(env, idx)   # keep the inputs alive
+    env._lib.check(env.lib.tb_gather_rows(env.ptr(du), env.ptr(dl), d, env.ptr(di), m, env.ptr(au), env.ptr(al),
+                                          env.sp()))
     np.testing.assert_array_equal(au.cpu().numpy(), u[idx])
     np.testing.assert_array_equal(al.cpu().numpy(), l[idx])
 
@@ -208,10 +211,11 @@ def test_volume_variation_matches_oracle(env, d):
     u = rng.random((n, d))
     w = np.exp(-0.5 * rng.chisquare(4, n))
     w /= w.sum()
-    got = env.k.volume_variation(dev_arr(env, u), dev_arr(env, w), n, d)
+    du, dw = dev_arr(env, u), dev_arr(env, w)
+    got = env.k.volume_variation(du, dw, n, d)
     assert got == pytest.approx(po.volume_variation(u, w), rel=1e-9)
     # too few samples -> 1e10 (tools.py:87-88)
-    assert env.k.volume_variation(dev_arr(env, u[:d]), dev_arr(env, w[:d]), d, d) == 1e10
+    assert env.k.volume_variation(du, dw, d, d) == 1e10
 
 
 def test_volume_variation_rank_deficient_regularises(env):
@@ -222,7 +226,8 @@ def test_volume_variation_rank_deficient_regularises(env):
     u = rng.random((n, d))
     u[:, 3] = u[:, 0]                       # exactly collinear -> matrix_rank < d
     w = np.full(n, 1.0 / n)
-    got = env.k.volume_variation(dev_arr(env, u), dev_arr(env, w), n, d)
+    du, dw = dev_arr(env, u), dev_arr(env, w)
+    got = env.k.volume_variation(du, dw, n, d)
     assert got == pytest.approx(po.volume_variation(u, w), rel=1e-6)
 
 
@@ -263,8 +268,8 @@ def test_select_ranks_exact(env):
     ranks = np.array([m_total // 2 - 1, m_total // 2], dtype=np.int64)
     out = torch.empty(2 * d, dtype=torch.float64, device=env.dev)
     ws = torch.zeros(env.lib.tb_select_workspace_bytes(d, 2), dtype=torch.uint8, device=env.dev)
-    env._lib.check(env.lib.tb_select_ranks(env.ptr(dev_arr(env, u)), env.ptr(dev_arr(env, rows)), d, 2000, d,
-                                           env.ptr(dev_arr(env, mult)), env.ptr(dev_arr(env, ranks)), 2,
+    du, dr, dm, dk = dev_arr(env, u), dev_arr(env, rows), dev_arr(env, mult), dev_arr(env, ranks)
+    env._lib.check(env.lib.tb_select_ranks(env.ptr(du), env.ptr(dr), d, 2000, d, env.ptr(dm), env.ptr(dk), 2,
                                            env.ptr(ws), env.ptr(out), env.sp()))
     expanded = np.repeat(u[rows], mult, axis=0)
     srt = np.sort(expanded, axis=0)
@@ -277,8 +282,8 @@ def test_chol_inv_and_regularisation(env, d):
     a = rng.normal(size=(d, d))
     spd = a @ a.T / d + 0.1 * np.eye(d)
     bad = spd.copy()
-    bad[:, -1] = bad[:, 0]
-    bad[-1, :] = bad[0, :]                           # singular -> regularised (modes.py:114-119)
+    bad[:, -1] = 0.0
+    bad[-1, :] = 0.0                                 # exact zero pivot -> LinAlgError -> regularised (modes.py:114-119)
     mats = np.stack([spd, bad]) if d > 1 else np.stack([spd, np.zeros((1, 1))])
     dm = dev_arr(env, mats)
     chol = torch.empty_like(dm)
@@ -321,8 +326,9 @@ def test_prior_draw_and_likelihoods_bit_exact(env):
         u = torch.empty((n, d), dtype=torch.float64, device=env.dev)
         x = torch.empty((n, d), dtype=torch.float64, device=env.dev)
         logl = torch.empty(n, dtype=torch.float64, device=env.dev)
-        env._lib.check(env.lib.tb_prior_draw(n, C.byref(p), env.ptr(dev_arr(env, tape_u)), env.ptr(u), env.ptr(x),
-                                             env.ptr(logl), env.sp()))
+        dt = dev_arr(env, tape_u)
+        env._lib.check(env.lib.tb_prior_draw(n, C.byref(p), env.ptr(dt), env.ptr(u), env.ptr(x), env.ptr(logl),
+                                             env.sp()))
         np.testing.assert_array_equal(u.cpu().numpy(), tape_u)
         x_ref = np.array([prior(r) for r in tape_u])
         np.testing.assert_array_equal(x.cpu().numpy(), x_ref)
