@@ -227,6 +227,10 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
                   double* u, double* logl, double* qcur, void* workspace, double* ctrl,
                   int32_t count, tb_stream_t stream);
 
+/* testing hook: route every n_dim through the generic (runtime-d) step kernel instead of the
+ * compile-time-d fast path (tape mode must give identical decisions on both) */
+int tb_set_mcmc_generic(int32_t on);
+
 /* out[i] = uniform [0,1) number i+offset of stream (seed, iteration, purpose): the draws the
  * host-driven resampling / training steps consume in Philox mode (purpose 4 / 5) */
 int tb_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t purpose, int64_t offset,

@@ -75,6 +75,7 @@ SIGNATURES = {
     "tb_mcmc_steps": (c_i32, [c_i64, C.POINTER(TbMcmcParams), C.POINTER(TbTape), PTR, PTR, PTR, PTR,
                               PTR, PTR, c_i32, PTR]),
     "tb_philox_uniform": (c_i32, [c_u64, c_u64, c_u32, c_i64, c_i64, PTR, PTR]),
+    "tb_set_mcmc_generic": (c_i32, [c_i32]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -126,6 +126,22 @@ def test_full_run_matches_oracle_on_tapes(name):
     np.testing.assert_array_equal(st.get_history("steps"), g["h_steps"])
 
 
+def test_generic_step_kernel_matches_oracle_on_tapes():
+    """The runtime-d kernel (used for n_dim without a compile-time instantiation) on the same tapes."""
+    from tempest_b200 import _lib
+
+    lib = _lib.load()
+    lib.tb_set_mcmc_generic(1)
+    try:
+        o, s, _ = run_pair("rosen10_n64_tpcn_mult", max_iterations=12)
+    finally:
+        lib.tb_set_mcmc_generic(0)
+    np.testing.assert_array_equal(s.state.get_history("beta"), np.array(o.hist["beta"]))
+    np.testing.assert_array_equal(s.state.get_history("steps"), np.array(o.hist["steps"]))
+    np.testing.assert_allclose(s.state.get_history("u"), np.array(o.hist["u"]), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(s.state.get_history("logl"), np.array(o.hist["logl"]), rtol=1e-9, atol=1e-9)
+
+
 def test_host_driven_search_equals_device_search():
     import tempest_b200 as tp
 
