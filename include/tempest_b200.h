@@ -118,7 +118,7 @@ int tb_weighted_moments(const double* u, const double* w, int64_t n, int32_t d,
  * ref: tools.py:111-115 */
 int tb_mahalanobis_cv(const double* u, const double* w, int64_t n, int32_t d,
                       const double* mean, const double* cov_inv, void* workspace,
-                      double* cv_out, tb_stream_t stream);
+                      double* cv_out2 /* {cv, raw sum} */, tb_stream_t stream);
 /* batched d x d Cholesky + inverse with the reference's regularise-on-failure rule
  * (modes.py:105-119): on a non-positive pivot add max(1e-6, 1e-6*|tr|) to the diagonal (the
  * regularised matrix is written back to `a`) and retry.  info[k] = 0 ok, 1 regularised,
@@ -189,6 +189,7 @@ typedef struct tb_mcmc_params {
   int32_t n_dim, n_modes, sampler, rng_mode;
   int32_t like_id, prior_id;
   int32_t n_steps, n_max;          /* per-dimension base / max step counts (config.py:80-84) */
+  int32_t defer_update, reserved;  /* 1: sharded run, leave per-step totals for an all-reduce + tb_mcmc_update */
   double beta;
   uint64_t seed, iteration;         /* Philox key material */
   int64_t slot_offset;              /* global slot id of local walker 0 (multi-GPU) */
@@ -226,6 +227,27 @@ int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, con
 int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign,
                   double* u, double* logl, double* qcur, void* workspace, double* ctrl,
                   int32_t count, tb_stream_t stream);
+
+/* ---- entry points used when particles are sharded over GPUs ---------------------- */
+/* multinomial search inside a global cdf: this shard's cdf starts at `offset`, the global total is
+ * `total`; idx = local ancestor index or -1 when the draw belongs to another shard */
+int tb_search_right_sharded(const double* cdf, int64_t n, double offset, double total, int32_t is_first,
+                            const double* draws, int64_t m, int64_t* idx, tb_stream_t stream);
+/* w /= denom */
+int tb_scale_inplace(double* w, int64_t n, double denom, tb_stream_t stream);
+/* one stage of tb_select_ranks: 0 init, 1 local histogram of `level`, 2 pick from the (all-reduced)
+ * histogram, 3 write results; the histogram lives at workspace + tb_select_hist_offset() */
+int tb_select_stage(const double* base, const int64_t* rows, int64_t stride, int64_t n, int32_t ncols,
+                    const int32_t* mult, const int64_t* ranks, int32_t nranks, void* workspace, double* out,
+                    int32_t stage, int32_t level, tb_stream_t stream);
+size_t tb_select_hist_offset(int32_t ncols, int32_t nranks);
+/* moments with explicit control: exactly one of w / mult is non-NULL; do_mean writes
+ * mean = inv_norm * sum w x (a partial sum when sharded), do_cov the scatter about `mean` */
+int tb_moments_partial(const double* u, const int64_t* rows, const double* w, const int32_t* mult, int64_t n,
+                       int32_t d, double inv_norm, int32_t do_mean, int32_t do_cov, void* workspace,
+                       double* mean, double* cov, tb_stream_t stream);
+/* apply sigma adaptation + stop rule from all-reduced per-step totals (defer_update = 1) */
+int tb_mcmc_update(const tb_mcmc_params* p, double* ctrl, tb_stream_t stream);
 
 /* testing hook: route every n_dim through the generic (runtime-d) step kernel instead of the
  * compile-time-d fast path (tape mode must give identical decisions on both) */

@@ -26,6 +26,7 @@ class TbMcmcParams(C.Structure):
     _fields_ = [
         ("n_dim", c_i32), ("n_modes", c_i32), ("sampler", c_i32), ("rng_mode", c_i32),
         ("like_id", c_i32), ("prior_id", c_i32), ("n_steps", c_i32), ("n_max", c_i32),
+        ("defer_update", c_i32), ("reserved", c_i32),
         ("beta", c_f64), ("seed", c_u64), ("iteration", c_u64), ("slot_offset", c_i64),
         ("n_global", c_i64), ("like_params", PTR), ("prior_params", PTR), ("mode_mean", PTR),
         ("mode_chol", PTR), ("mode_inv", PTR), ("mode_dof", PTR), ("bc_kind", PTR),
@@ -76,6 +77,12 @@ SIGNATURES = {
                               PTR, PTR, c_i32, PTR]),
     "tb_philox_uniform": (c_i32, [c_u64, c_u64, c_u32, c_i64, c_i64, PTR, PTR]),
     "tb_set_mcmc_generic": (c_i32, [c_i32]),
+    "tb_search_right_sharded": (c_i32, [PTR, c_i64, c_f64, c_f64, c_i32, PTR, c_i64, PTR, PTR]),
+    "tb_scale_inplace": (c_i32, [PTR, c_i64, c_f64, PTR]),
+    "tb_select_stage": (c_i32, [PTR, PTR, c_i64, c_i64, c_i32, PTR, PTR, c_i32, PTR, PTR, c_i32, c_i32, PTR]),
+    "tb_select_hist_offset": (SIZE, [c_i32, c_i32]),
+    "tb_moments_partial": (c_i32, [PTR, PTR, PTR, PTR, c_i64, c_i32, c_f64, c_i32, c_i32, PTR, PTR, PTR, PTR]),
+    "tb_mcmc_update": (c_i32, [C.POINTER(TbMcmcParams), PTR, PTR]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -110,7 +117,8 @@ KERNELS_PER_CALL = {
     "tb_student_sigma": 1, "tb_median_pairs": 1, "tb_add_trace_reg": 1, "tb_normalize_inplace": 2,
     "tb_binade_hist": 1, "tb_masked_sums": 1, "tb_compact_ge": 3, "tb_select_ranks": 14, "tb_count_indices": 1,
     "tb_counted_moments": 2, "tb_prior_draw": 1, "tb_transform": 1, "tb_mcmc_begin": 2,
-    "tb_mcmc_steps": lambda args: int(args[9]), "tb_philox_uniform": 1,
+    "tb_mcmc_steps": lambda args: int(args[9]), "tb_philox_uniform": 1, "tb_search_right_sharded": 1,
+    "tb_scale_inplace": 1, "tb_select_stage": 1, "tb_moments_partial": 2, "tb_mcmc_update": 1,
 }
 launch_count = 0
 

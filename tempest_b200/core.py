@@ -15,6 +15,7 @@ import torch
 
 from . import _lib
 from .config import SamplerConfig
+from .dist import Comm, shard_bounds
 from .ensemble import DeviceState, PersistentEnsemble, ptr, stream_ptr
 from .registry import is_registry_likelihood, is_registry_prior
 from .rng import PhiloxSource
@@ -29,12 +30,23 @@ class SamplerCore:
             raise RuntimeError("tempest_b200 needs a CUDA device (sm_100a): there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = _lib.load()
-        self.k = Kernels(self.device)
-        self.ensemble = PersistentEnsemble(config.n_dim, self.device)
+        # particles shard over the ranks of an initialised torch.distributed job
+        self.comm = Comm()
+        self.n_global = config.n_particles
+        if self.comm.on:
+            from .sharded import ShardedKernels
+
+            if config.random_state is None:
+                raise ValueError("pass random_state on >1 GPU: every rank must draw the same replicated uniforms")
+            lo, hi = shard_bounds(self.n_global, self.comm.world, self.comm.rank)
+            self.slot_offset, self.n_local = lo, hi - lo
+            self.k = ShardedKernels(self.device, self.comm)
+        else:
+            self.slot_offset, self.n_local = 0, self.n_global
+            self.k = Kernels(self.device)
+        self.ensemble = PersistentEnsemble(config.n_dim, self.device, world=self.comm.world)
         self.state = DeviceState(config.n_dim, core=self)
         self.rng = PhiloxSource(config.random_state, self.device)
-        self.n_global = config.n_particles
-        self.slot_offset = 0
         self.trace: dict = {}
         self.n_mcmc_launches = 0
         self.n_total = 0
@@ -84,7 +96,7 @@ class SamplerCore:
     def weights_buffer(self) -> torch.Tensor:
         n = self.ensemble.n_total
         if self._weights is None or self._weights.numel() < n:
-            self._weights = torch.empty(max(int(n * 1.5), 1024), dtype=F64, device=self.device)
+            self._weights = torch.empty(max(int(n * 2), 1024), dtype=F64, device=self.device)
         return self._weights[:n]
 
     def mcmc_params(self, beta: float, mode_stats: Optional[ModeStats]) -> _lib.TbMcmcParams:
@@ -103,6 +115,7 @@ class SamplerCore:
         p.iteration = int(self.rng.iteration)
         p.slot_offset = self.slot_offset
         p.n_global = self.n_global
+        p.defer_update = 1 if self.comm.on else 0
         p.like_params = self._like_params.data_ptr()
         p.prior_params = self._prior_params.data_ptr()
         if mode_stats is not None:
@@ -226,6 +239,8 @@ class SamplerCore:
         if trim_importance_weights:                        # core.py:210-220
             idx, w = k.trim(w, n, ess=ess_trim, bins=bins_trim)
             u, logl = u[idx], logl[idx]
+        if resample and self.comm.on:
+            raise NotImplementedError("posterior(resample=True) is not sharded yet")
         if resample:                                       # core.py:222-231
             m = int(w.numel())
             cdf = k.cdf(w, m, "post_cdf")
@@ -234,6 +249,10 @@ class SamplerCore:
             u, logl = u[idx], logl[idx]
             w = torch.full((m,), 1.0 / m, dtype=F64, device=self.device)
         x = self.transform_to_x(u.contiguous())
+        if self.comm.on:                                   # every rank returns the global (rank-major) sample
+            x, w, logl = (self.comm.allgather_rows(t.contiguous()) for t in (x, w, logl))
+            if logw is not None:
+                logw = self.comm.allgather_rows(torch.as_tensor(logw).to(self.device)).cpu().numpy()
         out = (x.cpu().numpy(), w.cpu().numpy(), logl.cpu().numpy())
         return out + (logw,) if return_logw else out
 

@@ -13,6 +13,8 @@
 // proposals, normals and likelihood terms never leave registers.
 #include "tb_like.cuh"
 
+static int tb_force_generic_mcmc = 0;
+
 namespace {
 using namespace tb;
 
@@ -56,6 +58,8 @@ __device__ __forceinline__ double bc_apply(double v, int kind) {
   return v;
 }
 
+__device__ void apply_step_update(const tb_mcmc_params& p, double* ctrl, const double* tot, int K);
+
 // fold the per-CTA partials, adapt sigma and evaluate the stop rule (mcmc.py:180-194, 104-135)
 __device__ void finish_step(const StepArgs& a, int K, int nparts) {
   __shared__ double tot[kMaxModes + 3];
@@ -66,9 +70,18 @@ __device__ void finish_step(const StepArgs& a, int K, int nparts) {
     tot[c] = t;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double* ctrl = a.ctrl;
-    const int d = a.p.n_dim;
+  if (a.p.defer_update) {
+    // sharded run: leave this rank's totals for the host to all-reduce; tb_mcmc_update applies them
+    for (int c = threadIdx.x; c < W; c += blockDim.x) a.ctrl[C_BASE + 3 * K + c] = tot[c];
+    return;
+  }
+  if (threadIdx.x == 0) apply_step_update(a.p, a.ctrl, tot, K);
+}
+
+// adapt sigma and evaluate the stop rule from the (global) per-mode totals
+__device__ void apply_step_update(const tb_mcmc_params& p, double* ctrl, const double* tot, int K) {
+  {
+    const int d = p.n_dim;
     const int it = (int)ctrl[C_STEPS] + 1;
     const double sigma0 = 2.38 / sqrt((double)d);
     double* sigma = ctrl + C_BASE;
@@ -82,21 +95,21 @@ __device__ void finish_step(const StepArgs& a, int K, int nparts) {
       if (count[c] > 0.0) {
         const double mean_alpha = tot[c] / count[c];
         double s = sigma[c] + rate * (mean_alpha - 0.234);
-        if (a.p.sampler == TB_SAMPLE_TPCN) s = fmin(fmax(s, 0.0), fmin(sigma0, 0.99));
+        if (p.sampler == TB_SAMPLE_TPCN) s = fmin(fmax(s, 0.0), fmin(sigma0, 0.99));
         sigma[c] = s;
       }
     }
-    const double n_all = (double)a.p.n_global;
+    const double n_all = (double)p.n_global;
     const double acc = tot[K] / n_all;
     // weighted sigma over the first n_nonempty sigmas (reference quirk: sigmas[:len(sizes)])
     double sw = 0.0, ws = 0.0;
     int j = 0;
     for (int c = 0; c < K; ++c) if (count[c] > 0.0) { ws += sigma[j] * count[c]; sw += count[c]; ++j; }
     const double wsig = ws / sw;
-    const double n_min = (double)(a.p.n_steps * d);
+    const double n_min = (double)(p.n_steps * d);
     const double ratio = sigma0 / fmax(1e-6, wsig);
-    const double n_adapt = (double)(a.p.n_steps * d) * (0.234 / fmax(0.01, acc)) * (ratio * ratio);
-    const double n_cap = (double)(a.p.n_max * d);
+    const double n_adapt = (double)(p.n_steps * d) * (0.234 / fmax(0.01, acc)) * (ratio * ratio);
+    const double n_cap = (double)(p.n_max * d);
     const double n_final = fmin(fmax(n_min, n_adapt), n_cap);
     const int stop_at = (int)n_final;   // Python int() truncation
     ctrl[C_STEPS] = (double)it;
@@ -173,7 +186,21 @@ mcmc_step_fast(StepArgs a) {
     logl = a.logl[k];
     double cm = sig, keep = 0.0;
     if (tpcn) {
-      q = a.qcur[k];
+      if (step == 0) {     // first step of this mutation: q of the freshly resampled state
+        const double* IV = s_inv + c * D * D;
+        double dq[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) dq[i] = urow[i] - mu[i];
+        q = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double y = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) y += dq[i] * IV[i * D + j];
+          q += y * dq[j];
+        }
+        a.qcur[k] = q;
+      } else q = a.qcur[k];
       double g;
       if (tape) g = tape_over ? 1.0 : a.tape.gamma[(int64_t)step * a.n + k];
       else {   // Marsaglia-Tsang with the squeeze test; shape = (D + nu)/2 >= 1
@@ -541,10 +568,14 @@ mcmc_begin_kernel(int64_t n, tb_mcmc_params p, const int32_t* __restrict__ assig
   }
 }
 
+__global__ void mcmc_update_kernel(tb_mcmc_params p, double* __restrict__ ctrl) {
+  if (threadIdx.x == 0 && ctrl[C_DONE] == 0.0) apply_step_update(p, ctrl, ctrl + C_BASE + 3 * p.n_modes, p.n_modes);
+}
+
 __global__ void mcmc_init_ctrl_kernel(tb_mcmc_params p, double* __restrict__ ctrl) {
   const int K = p.n_modes;
   const double sigma0 = 2.38 / sqrt((double)p.n_dim);
-  for (int e = threadIdx.x; e < C_BASE + 3 * K; e += blockDim.x) {
+  for (int e = threadIdx.x; e < C_BASE + 4 * K + 3; e += blockDim.x) {
     double v = 0.0;
     if (e == C_SIGMA0) v = sigma0;
     if (e >= C_BASE && e < C_BASE + K) v = (p.sampler == TB_SAMPLE_TPCN) ? fmin(sigma0, 0.99) : sigma0;  // mcmc.py:222-223, 298-299
@@ -616,14 +647,16 @@ int launch_fast(const StepArgs& a, int count, cudaStream_t st) {
   return e == cudaSuccess ? TB_OK : (int)e;
 }
 
+inline bool has_fast_path(int d) {
+  return d == 2 || d == 3 || d == 4 || d == 5 || d == 6 || d == 8 || d == 10 || d == 12 || d == 16;
+}
+
 bool params_ok(int64_t n, const tb_mcmc_params* p) {
   return p && n > 0 && p->n_dim > 0 && p->n_dim <= 128 && p->n_modes > 0 && p->n_modes <= kMaxModes &&
          p->prior_params && p->like_params;
 }
 
 }  // namespace
-
-static int tb_force_generic_mcmc = 0;
 
 extern "C" {
 
@@ -633,7 +666,14 @@ size_t tb_mcmc_workspace_bytes(int64_t n, int32_t n_modes) {
   const int64_t grid = (n + kMcmcBlock - 1) / kMcmcBlock;
   return 256 + sizeof(double) * (size_t)grid * (n_modes + 3);
 }
-size_t tb_mcmc_ctrl_doubles(int32_t n_modes) { return C_BASE + 3 * (size_t)n_modes; }
+size_t tb_mcmc_ctrl_doubles(int32_t n_modes) { return C_BASE + 4 * (size_t)n_modes + 3; }
+
+int tb_mcmc_update(const tb_mcmc_params* p, double* ctrl, tb_stream_t stream) {
+  if (!p || !ctrl || p->n_modes <= 0 || p->n_modes > kMaxModes) return TB_ERR_ARG;
+  mcmc_update_kernel<<<1, 32, 0, as_stream(stream)>>>(*p, ctrl);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
 
 int tb_prior_draw(int64_t n, const tb_mcmc_params* p, const double* prior_u_tape, double* u, double* x,
                   double* logl, tb_stream_t stream) {
@@ -669,7 +709,9 @@ int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, con
   if (e != cudaSuccess) return (int)e;
   mcmc_init_ctrl_kernel<<<1, 256, 0, st>>>(*p, ctrl);
   const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);
-  mcmc_begin_kernel<<<grid, kMcmcBlock, 0, st>>>(n, *p, assign, u, p->sampler == TB_SAMPLE_TPCN ? qcur : nullptr, ctrl);
+  // the fast step kernel computes q itself on its first step
+  const bool need_q = p->sampler == TB_SAMPLE_TPCN && (tb_force_generic_mcmc || !has_fast_path(p->n_dim));
+  mcmc_begin_kernel<<<grid, kMcmcBlock, 0, st>>>(n, *p, assign, u, need_q ? qcur : nullptr, ctrl);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

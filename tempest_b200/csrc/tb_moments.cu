@@ -80,6 +80,11 @@ scale_reduce_kernel(double* __restrict__ w, int64_t n, const double* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(kBlock) scale_kernel(double* __restrict__ w, int64_t n, double denom) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = w[i] / denom;
+}
+
 // ---- binade histogram -------------------------------------------------------------------
 // bin = biased exponent (0..2047) of each non-negative weight; per-bin count, sum w, sum w^2.
 // CTA-private shared histograms (uniform warps take a shuffle-reduced fast path), one global
@@ -274,8 +279,10 @@ __global__ void sel_finish_kernel(const SelState* __restrict__ st, double* __res
 __global__ void __launch_bounds__(kBlock)
 count_indices_kernel(const int64_t* __restrict__ idx, int64_t m, int* __restrict__ counts) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride)
-    atomicAdd(&counts[__ldg(idx + k)], 1);
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+    const int64_t j = __ldg(idx + k);
+    if (j >= 0) atomicAdd(&counts[j], 1);     // -1: draw owned by another shard
+  }
 }
 
 // ---- weighted / counted moments -----------------------------------------------------------
@@ -460,7 +467,134 @@ mahal_cv_kernel(const double* __restrict__ u, const double* __restrict__ w, int6
     double t = 0.0;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(&ws->partial[i][0]);
     t = block_sum(t, red);
-    if (threadIdx.x == 0) out[0] = 0.5 * sqrt(t);
+    if (threadIdx.x == 0) { out[0] = 0.5 * sqrt(t); out[1] = t; }
+  }
+}
+
+// ---- small-d fast paths: one row per thread, everything in registers -----------------------------
+// scatter (upper triangle) of rows centred at `mean`; HBM-bound: each row is read once (8 d bytes).
+constexpr int kSmallBlock = 128;
+template <int D, typename WT>
+__global__ void __launch_bounds__(kSmallBlock)
+mom_cov_small_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, const WT* __restrict__ w,
+                     int64_t n, const double* __restrict__ mean, MomWs* ws, double* __restrict__ cov) {
+  constexpr int P = D * (D + 1) / 2;
+  __shared__ double red[kSmallBlock / 32][P];
+  double mu[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) mu[c] = mean[c];
+  double acc[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) acc[p] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const int64_t r = rows ? __ldg(rows + j) : j;
+    const double wj = wt_load(w, j);
+    const double* row = u + r * D;
+    double x[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) x[c] = __ldg(row + c) - mu[c];
+    int p = 0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const double xa = x[a] * wj;
+#pragma unroll
+      for (int b = a; b < D; ++b) { acc[p] += xa * x[b]; ++p; }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const double v = warp_sum(acc[p]);
+    if (lane == 0) red[wid][p] = v;
+  }
+  __syncthreads();
+  double* part = ws->partial + (size_t)blockIdx.x * P;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    double t = 0.0;
+    for (int q = 0; q < kSmallBlock / 32; ++q) t += red[q][p];
+    part[p] = t;
+  }
+  if (last_block_arrives(&ws->ticket)) {
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      double t = 0.0;
+      for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(ws->partial + (size_t)b * P + p);
+      int a = 0, rem = p;
+      while (rem >= D - a) { rem -= D - a; ++a; }
+      const int bcol = a + rem;
+      cov[a * D + bcol] = t;
+      cov[bcol * D + a] = t;
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kSmallBlock)
+mahal_small_kernel(const double* __restrict__ u, const double* __restrict__ w, int64_t n,
+                   const double* __restrict__ mean, const double* __restrict__ inv, ReduceWs* ws,
+                   double* __restrict__ out) {
+  __shared__ double sinv[D * D];
+  __shared__ double red[40];
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x) sinv[e] = inv[e];
+  double mu[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) mu[c] = mean[c];
+  __syncthreads();
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const double* row = u + j * D;
+    double x[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) x[c] = __ldg(row + c) - mu[c];
+    double d2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {          // (xc @ inv)[k] * xc[k], summed over k (tools.py:111)
+      double y = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) y += x[c] * sinv[c * D + k];
+      d2 += y * x[k];
+    }
+    double dev = d2 - (double)D;
+    dev = fmin(fmax(dev, -1e6), 1e6);
+    const double ww = __ldg(w + j);
+    acc += (ww * ww) * (dev * dev);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) ws->partial[blockIdx.x][0] = acc;
+  if (last_block_arrives(&ws->ticket)) {
+    double t = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(&ws->partial[i][0]);
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) { out[0] = 0.5 * sqrt(t); out[1] = t; }
+  }
+}
+
+inline int small_grid(int64_t n) {
+  int64_t need = (n + kSmallBlock - 1) / kSmallBlock;
+  int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+template <typename WT>
+bool launch_cov_small(int d, int grid, const double* u, const int64_t* rows, const WT* w, int64_t n,
+                      const double* mean, MomWs* ws, double* cov, cudaStream_t st) {
+  switch (d) {
+#define TB_CASE(DD) case DD: mom_cov_small_kernel<DD, WT><<<grid, kSmallBlock, 0, st>>>(u, rows, w, n, mean, ws, cov); return true;
+    TB_CASE(1) TB_CASE(2) TB_CASE(3) TB_CASE(4) TB_CASE(5) TB_CASE(6) TB_CASE(7) TB_CASE(8) TB_CASE(9) TB_CASE(10)
+#undef TB_CASE
+    default: return false;
+  }
+}
+
+inline bool launch_mahal_small(int d, int grid, const double* u, const double* w, int64_t n, const double* mean,
+                               const double* inv, ReduceWs* ws, double* out, cudaStream_t st) {
+  switch (d) {
+#define TB_CASE(DD) case DD: mahal_small_kernel<DD><<<grid, kSmallBlock, 0, st>>>(u, w, n, mean, inv, ws, out); return true;
+    TB_CASE(1) TB_CASE(2) TB_CASE(3) TB_CASE(4) TB_CASE(5) TB_CASE(6) TB_CASE(7) TB_CASE(8) TB_CASE(9) TB_CASE(10)
+    TB_CASE(12) TB_CASE(16)
+#undef TB_CASE
+    default: return false;
   }
 }
 
@@ -472,12 +606,14 @@ inline int mom_grid(int64_t n, int d) {
 
 template <typename WT>
 int launch_moments(const double* u, const int64_t* rows, const WT* w, int64_t n, int d, double inv_norm,
-                   void* workspace, double* mean, double* cov, cudaStream_t st) {
+                   void* workspace, double* mean, double* cov, cudaStream_t st, bool do_mean = true) {
   if (n <= 0 || d <= 0 || d > kMomMaxD || !u || !w || !workspace || !mean) return TB_ERR_ARG;
   MomWs* ws = (MomWs*)workspace;
   const int grid = mom_grid(n, d);
-  mom_mean_kernel<WT><<<grid, kBlock, 0, st>>>(u, rows, w, n, d, inv_norm, ws, mean);
-  if (cov) {
+  if (do_mean) mom_mean_kernel<WT><<<grid, kBlock, 0, st>>>(u, rows, w, n, d, inv_norm, ws, mean);
+  if (cov && launch_cov_small<WT>(d, small_grid(n), u, rows, w, n, mean, ws, cov, st)) {
+    // register-resident fast path (d <= 10)
+  } else if (cov) {
     const int P = d * (d + 1) / 2;
     const int tile_elems = kMomRows * d > 256 ? kMomRows * d : 256;
     size_t smem = sizeof(double) * (tile_elems + kMomRows + d) + sizeof(short) * 2 * P + 16;
@@ -574,6 +710,56 @@ int tb_select_ranks(const double* base, const int64_t* rows, int64_t stride, int
   return TB_OK;
 }
 
+int tb_select_stage(const double* base, const int64_t* rows, int64_t stride, int64_t n, int32_t ncols,
+                    const int32_t* mult, const int64_t* ranks, int32_t nranks, void* workspace, double* out,
+                    int32_t stage, int32_t level, tb_stream_t stream) {
+  if (ncols <= 0 || nranks <= 0 || nranks > 4 || !workspace || level < 0 || level >= kSelLevels) return TB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  SelState* state = (SelState*)workspace;
+  size_t off = (sizeof(SelState) * (size_t)ncols * nranks + 255) / 256 * 256;
+  unsigned int* hist = (unsigned int*)((char*)workspace + off);
+  const int slots = ncols * nranks;
+  if (stage == 0) {
+    if (!ranks) return TB_ERR_ARG;
+    sel_init_kernel<<<(slots + 255) / 256, 256, 0, st>>>(state, ranks, ncols, nranks);
+  } else if (stage == 1) {      // local histogram of this level (callers all-reduce it across ranks before stage 2)
+    cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (size_t)slots * kSelBins, st);
+    if (n > 0) {
+      if (!base) return TB_ERR_ARG;
+      const int grid = stream_grid(n * ncols, kBlock * 4, 8);
+      sel_hist_kernel<<<grid, kBlock, 0, st>>>(base, rows, stride, n, ncols, mult, state, nranks, level, hist);
+    }
+  } else if (stage == 2) {
+    sel_pick_kernel<<<slots, 256, 0, st>>>(state, hist, level);
+  } else if (stage == 3) {
+    if (!out) return TB_ERR_ARG;
+    sel_finish_kernel<<<(slots + 255) / 256, 256, 0, st>>>(state, out, slots);
+  } else return TB_ERR_ARG;
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+size_t tb_select_hist_offset(int32_t ncols, int32_t nranks) {
+  return (sizeof(SelState) * (size_t)ncols * nranks + 255) / 256 * 256;
+}
+
+int tb_scale_inplace(double* w, int64_t n, double denom, tb_stream_t stream) {
+  if (n <= 0 || !w) return TB_ERR_ARG;
+  scale_kernel<<<stream_grid(n, kBlock, 16), kBlock, 0, as_stream(stream)>>>(w, n, denom);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_moments_partial(const double* u, const int64_t* rows, const double* w, const int32_t* mult, int64_t n,
+                       int32_t d, double inv_norm, int32_t do_mean, int32_t do_cov, void* workspace, double* mean,
+                       double* cov, tb_stream_t stream) {
+  if ((w == nullptr) == (mult == nullptr)) return TB_ERR_ARG;
+  if (w) return launch_moments<double>(u, rows, w, n, d, inv_norm, workspace, mean, do_cov ? cov : nullptr,
+                                       as_stream(stream), do_mean != 0);
+  return launch_moments<int32_t>(u, rows, mult, n, d, inv_norm, workspace, mean, do_cov ? cov : nullptr,
+                                 as_stream(stream), do_mean != 0);
+}
+
 int tb_count_indices(const int64_t* idx, int64_t m, int32_t* counts, int64_t n, tb_stream_t stream) {
   if (m < 0 || n <= 0 || !counts || (m > 0 && !idx)) return TB_ERR_ARG;
   cudaStream_t st = as_stream(stream);
@@ -604,6 +790,10 @@ int tb_counted_moments(const double* u, const int64_t* rows, const int32_t* mult
 int tb_mahalanobis_cv(const double* u, const double* w, int64_t n, int32_t d, const double* mean,
                       const double* cov_inv, void* workspace, double* cv_out, tb_stream_t stream) {
   if (n <= 0 || d <= 0 || d > kMomMaxD || !u || !w || !mean || !cov_inv || !workspace || !cv_out) return TB_ERR_ARG;
+  if (launch_mahal_small(d, small_grid(n), u, w, n, mean, cov_inv, (ReduceWs*)workspace, cv_out, as_stream(stream))) {
+    TB_CHECK_LAUNCH();
+    return TB_OK;
+  }
   const int ld = d | 1;
   const int rt = d <= 32 ? kBlock : 64;
   size_t smem = sizeof(double) * ((size_t)d * d + d + (size_t)rt * ld);

@@ -36,7 +36,10 @@ struct CdfWs {
   double* tile_start;  // [nt] exact running sum BEFORE the tile's first element (easy tiles)
   long long* tile_F;   // [nt] integer total of the tile / later: within-run exclusive prefix
   int* tile_E;         // [nt] binade hypothesis or kHard
-  int* run_len;        // [nt] at run heads: number of tiles in the run
+  int* run_head;       // [nt] first tile of the run an easy tile belongs to
+  int* run_next;       // [nt] at run heads: first tile after the run
+  // after K4a: tile_sum[head] holds the run's integer total (bit pattern), tile_start[head] the
+  // exact running sum at the run's first element (written by the walker)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -49,7 +52,8 @@ __host__ __device__ inline CdfWs carve(void* base, int64_t nt) {
   w.tile_start = reinterpret_cast<double*>(p + o);   o += align_up(sizeof(double) * nt, 256);
   w.tile_F = reinterpret_cast<long long*>(p + o);    o += align_up(sizeof(long long) * nt, 256);
   w.tile_E = reinterpret_cast<int*>(p + o);          o += align_up(sizeof(int) * nt, 256);
-  w.run_len = reinterpret_cast<int*>(p + o);
+  w.run_head = reinterpret_cast<int*>(p + o);        o += align_up(sizeof(int) * nt, 256);
+  w.run_next = reinterpret_cast<int*>(p + o);
   return w;
 }
 
@@ -150,51 +154,58 @@ cdf_tile_inc_kernel(const double* __restrict__ p, int64_t n, CdfWs w) {
 }
 
 // ---- K4a: segmented exclusive prefix of tile_F over runs of equal E (single CTA) ---------
+// Also records, per run, its head tile, the tile after it and its integer total, so that the
+// walker (K4b) visits one entry per RUN instead of one per tile.
 __global__ void __launch_bounds__(1024)
 cdf_run_prefix_kernel(CdfWs w, int64_t nt) {
   __shared__ long long tail_sum[1024];   // sum of the (open) last segment of each thread's chunk
   __shared__ int tail_E[1024];           // E of that segment (kHard if the chunk ends with a hard tile / is empty)
+  __shared__ int tail_head[1024];        // its first tile
   __shared__ int whole[1024];            // 1 if the chunk is a single easy segment (no boundary inside)
   __shared__ long long carry_in[1024];
   __shared__ int carry_E[1024];
+  __shared__ int carry_head[1024];
   const int tid = threadIdx.x;
   const int64_t per = (nt + blockDim.x - 1) / blockDim.x;
   const int64_t lo = (int64_t)tid * per, hi = (lo + per < nt) ? lo + per : nt;
   {
-    long long s = 0; int curE = kHard; int single = 1; bool first = true;
+    long long s = 0; int curE = kHard; int single = 1; bool first = true; int head = -1;
     for (int64_t t = lo; t < hi; ++t) {
       int E = w.tile_E[t];
-      if (first) { curE = E; first = false; s = 0; if (E == kHard) single = 0; }
-      else if (E != curE || E == kHard) { single = 0; curE = E; s = 0; }
+      if (first) { curE = E; first = false; s = 0; head = (int)t; if (E == kHard) { single = 0; head = -1; } }
+      else if (E != curE || E == kHard) { single = 0; curE = E; s = 0; head = (E == kHard) ? -1 : (int)t; }
       if (E != kHard) s += w.tile_F[t];
     }
-    tail_sum[tid] = s; tail_E[tid] = (lo < hi) ? curE : kHard; whole[tid] = (lo < hi) ? single : 0;
-    if (lo >= hi) { tail_sum[tid] = 0; }
+    tail_sum[tid] = (lo < hi) ? s : 0; tail_E[tid] = (lo < hi) ? curE : kHard;
+    tail_head[tid] = (lo < hi) ? head : -1; whole[tid] = (lo < hi) ? single : 0;
   }
   __syncthreads();
   if (tid == 0) {
-    long long c = 0; int cE = kHard;   // running open segment entering chunk i
+    long long c = 0; int cE = kHard, cH = -1;   // open segment entering chunk i
     for (int i = 0; i < (int)blockDim.x; ++i) {
-      carry_in[i] = c; carry_E[i] = cE;
+      carry_in[i] = c; carry_E[i] = cE; carry_head[i] = cH;
       int64_t l = (int64_t)i * per;
       if (l >= nt) break;
       if (whole[i] && tail_E[i] == cE && cE != kHard) c += tail_sum[i];
-      else { c = tail_sum[i]; cE = tail_E[i]; }
+      else { c = tail_sum[i]; cE = tail_E[i]; cH = tail_head[i]; }
     }
   }
   __syncthreads();
-  {
-    long long s = carry_in[tid]; int curE = carry_E[tid];
+  if (lo < hi) {
+    long long s = carry_in[tid]; int curE = carry_E[tid]; int head = carry_head[tid];
     for (int64_t t = lo; t < hi; ++t) {
       int E = w.tile_E[t];
-      if (E == kHard) { curE = kHard; s = 0; w.run_len[t] = 1; continue; }
-      if (E != curE) { curE = E; s = 0; }
+      if (E == kHard || E != curE) {            // the open run (if any) ends right before t
+        if (curE != kHard && head >= 0) { w.run_next[head] = (int)t; w.tile_sum[head] = __longlong_as_double(s); }
+        if (E == kHard) { curE = kHard; head = -1; s = 0; continue; }
+        curE = E; head = (int)t; s = 0;
+      }
       long long f = w.tile_F[t];
       w.tile_F[t] = s;            // exclusive within-run prefix
-      // stash the tile total in tile_start (bit pattern) for the walker
-      w.tile_start[t] = __longlong_as_double(f);
+      w.run_head[t] = head;
       s += f;
     }
+    if (hi == nt && curE != kHard && head >= 0) { w.run_next[head] = (int)nt; w.tile_sum[head] = __longlong_as_double(s); }
   }
 }
 
@@ -259,30 +270,16 @@ cdf_walk_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ cd
       ++t;
       continue;
     }
-    // run of easy tiles with hypothesis E starting at t: find its end (warp-parallel scan ahead)
-    int64_t t1 = t + 1;
-    for (;;) {
-      int64_t c = t1 + lane;
-      bool same = (c < nt) && (w.tile_E[c] == E);
-      unsigned m = __ballot_sync(0xffffffffu, same);
-      if (m == 0xffffffffu) { t1 += 32; continue; }
-      t1 += __ffs(~m) - 1;
-      break;
-    }
-    // validate the hypothesis against the exact running sum
+    // t heads a run of easy tiles with hypothesis E: validate it against the exact running sum
+    const int64_t t1 = w.run_next[t];
+    const long long total = __double_as_longlong(w.tile_sum[t]);
     bool valid = have && s >= 2.2250738585072014e-308 && exponent_of(s) == E;
-    long long S0 = 0;
     if (valid) {
-      S0 = __double2ll_rn(s * pow2(52 - E));
-      const long long total = w.tile_F[t1 - 1] + __double_as_longlong(w.tile_start[t1 - 1]);
+      const long long S0 = __double2ll_rn(s * pow2(52 - E));
       valid = (S0 + total) < (1LL << 53);
       if (valid) {
-        const double q = pow2(E - 52);
-        for (int64_t c = t + lane; c < t1; c += 32) {
-          // exact start of every tile of the run; K5 finishes the tiles
-          w.tile_start[c] = (double)(S0 + w.tile_F[c]) * q;
-        }
-        s = (double)(S0 + total) * q;
+        if (lane == 0) w.tile_start[t] = s;       // exact running sum entering the run; K5 finishes the tiles
+        s = (double)(S0 + total) * pow2(E - 52);
         t = t1;
         continue;
       }
@@ -303,7 +300,7 @@ cdf_emit_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ cd
   const int E = w.tile_E[blockIdx.x];
   if (E == kHard) return;
   const double up = pow2(52 - E), top = pow2(E + 1), q = pow2(E - 52);
-  const long long S0 = __double2ll_rn(w.tile_start[blockIdx.x] * up);
+  const long long S0 = __double2ll_rn(w.tile_start[w.run_head[blockIdx.x]] * up) + w.tile_F[blockIdx.x];
   const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * (kTile / kTileThreads);
   long long inc[kTile / kTileThreads];
   long long mine = 0;
@@ -351,6 +348,25 @@ search_right_kernel(const double* __restrict__ cdf, int64_t n, const double* __r
   }
 }
 
+// sharded multinomial search: this shard's cdf is offset by `offset` inside a global cdf of total
+// `total`; idx = local ancestor index, or -1 when the draw belongs to another shard.
+__global__ void __launch_bounds__(kBlock)
+search_right_sharded_kernel(const double* __restrict__ cdf, int64_t n, double offset, double total, int is_first,
+                            const double* __restrict__ draws, int64_t m, int64_t* __restrict__ idx) {
+  const double lo_edge = __ddiv_rn(offset, total);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+    const double u = __ldg(draws + k);
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (__ddiv_rn(__dadd_rn(offset, __ldg(cdf + mid)), total) <= u) lo = mid + 1; else hi = mid;
+    }
+    const bool mine = (lo < n) && (is_first || lo_edge <= u);
+    idx[k] = mine ? lo : -1;
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
 systematic_kernel(const double* __restrict__ cdf, int64_t n, double u0, int64_t m, int64_t* __restrict__ idx,
                   int* __restrict__ overflow) {
@@ -389,7 +405,7 @@ size_t tb_cdf_workspace_bytes(int64_t n) {
   int64_t nt = (n + kTile - 1) / kTile;
   if (nt < 1) nt = 1;
   return align_up(sizeof(double) * nt, 256) * 2 + align_up(sizeof(long long) * nt, 256) +
-         align_up(sizeof(int) * nt, 256) * 2 + 256;
+         align_up(sizeof(int) * nt, 256) * 3 + 256;
 }
 
 int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_stream_t stream) {
@@ -420,6 +436,16 @@ int tb_search_right(const double* cdf, int64_t n, const double* draws, int64_t m
   if (n <= 0 || m < 0 || !cdf || (m > 0 && (!draws || !idx))) return TB_ERR_ARG;
   if (m == 0) return TB_OK;
   search_right_kernel<<<stream_grid(m, kBlock, 16), kBlock, 0, as_stream(stream)>>>(cdf, n, draws, m, idx);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_search_right_sharded(const double* cdf, int64_t n, double offset, double total, int32_t is_first,
+                            const double* draws, int64_t m, int64_t* idx, tb_stream_t stream) {
+  if (n <= 0 || m < 0 || !cdf || (m > 0 && (!draws || !idx))) return TB_ERR_ARG;
+  if (m == 0) return TB_OK;
+  search_right_sharded_kernel<<<stream_grid(m, kBlock, 16), kBlock, 0, as_stream(stream)>>>(cdf, n, offset, total,
+                                                                                          is_first, draws, m, idx);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

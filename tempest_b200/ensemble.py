@@ -43,9 +43,11 @@ def ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 class PersistentEnsemble:
     """All particles ever drawn, resident in HBM."""
 
-    def __init__(self, n_dim: int, device: torch.device, capacity: int = 0):
+    def __init__(self, n_dim: int, device: torch.device, capacity: int = 0, world: int = 1):
         self.n_dim = int(n_dim)
         self.device = device
+        self.world = int(world)          # shards of equal size: global counts = local counts * world
+        self.gen_n_local: List[int] = []
         self.lib = _lib.load()
         self.n_total = 0
         self.cap = 0
@@ -87,6 +89,10 @@ class PersistentEnsemble:
     def T(self) -> int:
         return len(self.gen_beta)
 
+    @property
+    def n_total_global(self) -> int:
+        return self.n_total * self.world
+
     # -- append one generation (commit, state_manager.py:356-416) -------------------------
     def append(self, u_new: torch.Tensor, logl_new: torch.Tensor, beta: float, logz: float) -> None:
         n_new = int(logl_new.shape[0])
@@ -96,7 +102,8 @@ class PersistentEnsemble:
         self.logl[n_old:n_old + n_new].copy_(logl_new)
         self.gen_beta.append(float(beta))
         self.gen_logz.append(float(logz))
-        self.gen_n.append(n_new)
+        self.gen_n.append(n_new * self.world)      # the mixture weights n_t / N use GLOBAL counts
+        self.gen_n_local.append(n_new)
         self._sync_gens()
         g = self._dev_gens
         _lib.check(self.lib.tb_mixture_append(
@@ -181,7 +188,7 @@ class DeviceState:
         else:
             flat = self._core.transform_to_x(ens.u[: ens.n_total]).cpu().numpy()
         out, o = [], 0
-        for n in ens.gen_n:
+        for n in ens.gen_n_local:
             out.append(flat[o:o + n].copy())
             o += n
         return out

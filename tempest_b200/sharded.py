@@ -1,0 +1,204 @@
+"""Multi-GPU (sharded ensemble) variants of the device steps: the same kernels on each rank's
+shard, with the handful of global reductions of SURVEY 8e carried by NCCL (see dist.py).
+
+Results do not depend on the number of GPUs beyond fp64 summation order: Philox counters are keyed
+by GLOBAL walker slot, the uniforms of the resampling / training draws are replicated, and every
+decision is taken from all-reduced quantities that are bitwise identical on all ranks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .dist import Comm, exchange_owned_rows, merge_ess_triples
+from .ensemble import PersistentEnsemble, ptr, stream_ptr
+from .steps import _EPS, F64, Kernels
+
+
+class ShardedKernels(Kernels):
+    def __init__(self, device: torch.device, comm: Comm):
+        super().__init__(device)
+        self.comm = comm
+        self.sharded = True
+
+    # -- reweighting: merge the per-shard (m, S1, S2) triples in rank order -------------------------
+    def probe(self, ens: PersistentEnsemble, beta: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = super().probe(ens, beta, out)
+        allp = self.comm.allgather(out[:6]).cpu().numpy()
+        m, s1, s2 = merge_ess_triples(allp[:, :3])
+        merged = [m, s1, s2, s1 * s1 / s2, m + math.log(s1), float(allp[:, 5].sum())]
+        out[:6].copy_(torch.tensor(merged, dtype=F64))
+        return out
+
+    # -- hooks used by Kernels.trim -------------------------------------------------------------------
+    def g_int(self, value: int) -> int:
+        t = torch.tensor([int(value)], dtype=torch.int64, device=self.device)
+        return int(self.comm.allreduce_sum_(t).item())
+
+    def g_sum3(self, vals, m: int, thr: float):
+        out3 = self.ws.f64("trim_m3", 3)
+        if m > 0:
+            _lib.check(self.lib.tb_masked_sums(ptr(vals), m, float(thr), ptr(self._reduce_ws), ptr(out3),
+                                               stream_ptr()), "tb_masked_sums")
+        else:
+            out3.zero_()
+        c, a1, a2 = self.comm.allreduce_sum_(out3).cpu().numpy()
+        return float(c), float(a1), float(a2)
+
+    def g_normalize(self, w, n: int):
+        _, s1, s2 = self.g_sum3(w, n, -math.inf)
+        _lib.check(self.lib.tb_scale_inplace(ptr(w), n, s1, stream_ptr()), "tb_scale_inplace")
+        return s1, s2 / (s1 * s1)
+
+    def g_hist(self, w, n: int):
+        cnt = self.ws.i64("trim_cnt", 2048)
+        s1 = self.ws.f64("trim_s1", 2048)
+        s2 = self.ws.f64("trim_s2", 2048)
+        _lib.check(self.lib.tb_binade_hist(ptr(w), n, ptr(cnt), ptr(s1), ptr(s2), stream_ptr()), "tb_binade_hist")
+        for t in (cnt, s1, s2):
+            self.comm.allreduce_sum_(t)
+        return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
+
+    def g_select(self, base, rows, stride, m, ncols, mult, ranks, nranks, out):
+        """Distributed radix select: local histograms, all-reduced per level, replicated picks."""
+        lib = self.lib
+        sws = self.ws.bytes("select", lib.tb_select_workspace_bytes(ncols, nranks))
+        off = int(lib.tb_select_hist_offset(ncols, nranks))
+        hist = sws[off: off + 4 * ncols * nranks * 2048].view(torch.int32)
+        args = (ptr(base), ptr(rows), stride, m, ncols, ptr(mult), ptr(ranks), nranks, ptr(sws), ptr(out))
+        st = stream_ptr()
+        _lib.check(lib.tb_select_stage(*args, 0, 0, st), "tb_select_stage")
+        for level in range(6):
+            _lib.check(lib.tb_select_stage(*args, 1, level, st), "tb_select_stage")
+            self.comm.allreduce_sum_(hist)
+            _lib.check(lib.tb_select_stage(*args, 2, level, st), "tb_select_stage")
+        _lib.check(lib.tb_select_stage(*args, 3, 0, st), "tb_select_stage")
+        return out
+
+    # -- volume variation: partial moments + all-reduce ------------------------------------------------
+    def volume_variation(self, u, w, n: int, d: int) -> float:
+        lib, st = self.lib, stream_ptr()
+        if n * self.comm.world < d + 1:
+            return 1e10
+        ws = self.ws.bytes("mom", lib.tb_moments_workspace_bytes(d))
+        mean = self.ws.f64("vv_mean", d)
+        cov = self.ws.f64("vv_cov", d * d)
+        _lib.check(lib.tb_moments_partial(ptr(u), None, ptr(w), None, n, d, 1.0, 1, 0, ptr(ws), ptr(mean), None, st),
+                   "tb_moments_partial")
+        self.comm.allreduce_sum_(mean)
+        _lib.check(lib.tb_moments_partial(ptr(u), None, ptr(w), None, n, d, 1.0, 0, 1, ptr(ws), ptr(mean), ptr(cov), st),
+                   "tb_moments_partial")
+        self.comm.allreduce_sum_(cov)
+        work = self.ws.f64("vv_work", d * d)
+        inv = self.ws.f64("vv_inv", d * d)
+        info = self.ws.i32("vv_info", 1)
+        norms = self.ws.f64("vv_norms", 3)
+        for attempt in range(2):
+            work.copy_(cov)
+            _lib.check(lib.tb_chol_inv(ptr(work), d, 1, None, ptr(inv), ptr(info), ptr(norms), st), "tb_chol_inv")
+            code = int(info.item())
+            nr = norms.cpu().numpy()
+            if attempt == 0:
+                singular = code != 0 or not np.isfinite(nr[:2]).all() or nr[0] * nr[1] >= 1.0 / (d * _EPS)
+            else:
+                singular = code == 2 or not np.isfinite(nr[:2]).all()
+            if not singular:
+                break
+            if attempt == 1:
+                return 1e10
+            _lib.check(lib.tb_add_trace_reg(ptr(cov), d, 1e-6, st), "tb_add_trace_reg")
+        out = self.ws.f64("vv_out", 2)
+        _lib.check(lib.tb_mahalanobis_cv(ptr(u), ptr(w), n, d, ptr(mean), ptr(inv), ptr(self._reduce_ws), ptr(out), st),
+                   "tb_mahalanobis_cv")
+        raw = self.comm.allreduce_sum_(out[1:2].clone())
+        return 0.5 * math.sqrt(float(raw.item()))
+
+    # -- global multinomial draws over the sharded cdf ---------------------------------------------------
+    def sharded_search(self, p: torch.Tensor, n: int, draws: torch.Tensor, out: torch.Tensor, name: str):
+        """Ancestor index of every (replicated) draw that falls in this rank's part of the global
+        cdf (rank-major concatenation), -1 elsewhere.  Returns (out, global total)."""
+        if n > 0 and p.numel() > 0:
+            cdf = self.cdf(p, n, name)
+            last = cdf[n - 1: n].clone()
+        else:                                   # this rank holds none of the candidates
+            n, cdf, last = 0, None, torch.zeros(1, dtype=F64, device=self.device)
+        totals = self.comm.allgather(last).flatten().cpu().numpy()
+        offset = float(np.sum(totals[: self.comm.rank])) if self.comm.rank else 0.0
+        total = float(np.sum(totals))
+        if n == 0:
+            out.fill_(-1)
+            return out, total
+        # "first" = first rank with a non-empty share (its lower edge is 0 by construction)
+        first = int(not np.any(totals[: self.comm.rank] > 0))
+        _lib.check(self.lib.tb_search_right_sharded(ptr(cdf), n, offset, total, first, ptr(draws),
+                                                    draws.numel(), ptr(out), stream_ptr()), "tb_search_right_sharded")
+        return out, total
+
+
+def sharded_mode_moments(core, idx, counts, n_trim_local: int, m_total: int, cmean, scatter):
+    """Count-weighted mean / scatter of the global resampled multiset (student.py:63)."""
+    k, ens, d = core.k, core.ensemble, core.ensemble.n_dim
+    lib, st = k.lib, stream_ptr()
+    mws = k.ws.bytes("mom", lib.tb_moments_workspace_bytes(d))
+    if n_trim_local:
+        _lib.check(lib.tb_moments_partial(ptr(ens.u), ptr(idx), None, ptr(counts), n_trim_local, d, 1.0 / m_total, 1, 0,
+                                          ptr(mws), ptr(cmean), None, st), "tb_moments_partial")
+    else:
+        cmean.zero_()
+    k.comm.allreduce_sum_(cmean)
+    if n_trim_local:
+        _lib.check(lib.tb_moments_partial(ptr(ens.u), ptr(idx), None, ptr(counts), n_trim_local, d, 1.0 / m_total, 0, 1,
+                                          ptr(mws), ptr(cmean), ptr(scatter), st), "tb_moments_partial")
+    else:
+        scatter.zero_()
+    k.comm.allreduce_sum_(scatter)
+
+
+def sharded_resample(core, weights: torch.Tensor, draws: torch.Tensor):
+    """N global multinomial draws; returns this rank's block of resampled (u, logl) rows."""
+    k, ens, comm = core.k, core.ensemble, core.comm
+    n_glob = core.n_global
+    d = ens.n_dim
+    idx = k.ws.i64("res_idx", n_glob)
+    k.sharded_search(weights, ens.n_total, draws, idx, "cdf")
+    own = torch.nonzero(idx >= 0).flatten()
+    rows = torch.empty((own.numel(), d + 1), dtype=F64, device=core.device)
+    if own.numel():
+        src = idx[own].contiguous()
+        u = torch.empty((own.numel(), d), dtype=F64, device=core.device)
+        l = torch.empty(own.numel(), dtype=F64, device=core.device)
+        _lib.check(k.lib.tb_gather_rows(ptr(ens.u), ptr(ens.logl), d, ptr(src), own.numel(), ptr(u), ptr(l),
+                                        stream_ptr()), "tb_gather_rows")
+        rows[:, :d] = u
+        rows[:, d] = l
+    lo, hi = core.slot_offset, core.slot_offset + core.n_local
+    mine = exchange_owned_rows(comm, rows, own, n_glob, lo, hi)
+    core.trace["resample_idx"] = idx
+    return mine[:, :d].contiguous(), mine[:, d].contiguous()
+
+
+def sharded_mcmc_loop(core, params, tape_ref, u, logl, qcur, ws, ctrl, n_min: int, n_cap: int, chunk: int):
+    """One Metropolis step per launch; the per-step totals (sum alpha per mode, accepted, proposals,
+    error) are all-reduced before sigma adaptation and the stop rule (tb_mcmc_update)."""
+    k, comm = core.k, core.comm
+    lib, sp = k.lib, stream_ptr()
+    K = params.n_modes
+    tot = ctrl[8 + 3 * K: 8 + 4 * K + 3]
+    launched = 0
+    next_check = n_min
+    while True:
+        _lib.check(lib.tb_mcmc_steps(core.n_local, C.byref(params), tape_ref, None, ptr(u), ptr(logl), ptr(qcur),
+                                     ptr(ws), ptr(ctrl), 1, sp), "tb_mcmc_steps")
+        comm.allreduce_sum_(tot)
+        _lib.check(lib.tb_mcmc_update(C.byref(params), ptr(ctrl), sp), "tb_mcmc_update")
+        launched += 1
+        if launched >= next_check or launched >= n_cap:
+            h = ctrl.cpu().numpy()
+            if h[1] != 0.0 or launched >= n_cap:
+                return h, launched
+            next_check = launched + chunk

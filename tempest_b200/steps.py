@@ -43,21 +43,21 @@ class Workspace:
     def f64(self, name: str, n: int) -> torch.Tensor:
         t = self._buf.get(name)
         if t is None or t.numel() < n:
-            t = torch.empty(max(int(n * 1.5), 16), dtype=F64, device=self.device)
+            t = torch.empty(max(int(n * 2), 16), dtype=F64, device=self.device)
             self._buf[name] = t
         return t[:n]
 
     def i64(self, name: str, n: int) -> torch.Tensor:
         t = self._buf.get(name)
         if t is None or t.numel() < n:
-            t = torch.empty(max(int(n * 1.5), 16), dtype=torch.int64, device=self.device)
+            t = torch.empty(max(int(n * 2), 16), dtype=torch.int64, device=self.device)
             self._buf[name] = t
         return t[:n]
 
     def i32(self, name: str, n: int) -> torch.Tensor:
         t = self._buf.get(name)
         if t is None or t.numel() < n:
-            t = torch.empty(max(int(n * 1.5), 16), dtype=torch.int32, device=self.device)
+            t = torch.empty(max(int(n * 2), 16), dtype=torch.int32, device=self.device)
             self._buf[name] = t
         return t[:n]
 
@@ -139,6 +139,7 @@ class Kernels:
         self._reduce_ws = self.ws.bytes("reduce", self.lib.tb_reduce_workspace_bytes())
         self.probe_out = torch.zeros(16, dtype=F64, device=device)
         self.n_probe_launches = 0
+        self.sharded = False
 
     # -- reweighting ----------------------------------------------------------------------
     def probe(self, ens: PersistentEnsemble, beta: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -193,7 +194,7 @@ class Kernels:
             if attempt == 1:
                 return 1e10
             _lib.check(self.lib.tb_add_trace_reg(ptr(cov), d, 1e-6, stream_ptr()), "tb_add_trace_reg")
-        out = self.ws.f64("vv_out", 1)
+        out = self.ws.f64("vv_out", 2)
         _lib.check(self.lib.tb_mahalanobis_cv(ptr(u), ptr(w), n, d, ptr(mean), ptr(inv), ptr(self._reduce_ws),
                                               ptr(out), stream_ptr()), "tb_mahalanobis_cv")
         return float(out.item())
@@ -218,6 +219,43 @@ class Kernels:
             raise IndexError("systematic resampling walked past the last weight (tools.py:223-225)")
         return out
 
+    # -- global reductions (overridden by sharded.ShardedKernels with all-reduces) -------------------
+    def g_int(self, value: int) -> int:
+        return int(value)
+
+    def g_normalize(self, w: torch.Tensor, n: int):
+        """w /= sum(w) in place (tools.py:36); returns (sum before, sum of squares after)."""
+        stats = self.ws.f64("trim_stats", 3)
+        _lib.check(self.lib.tb_normalize_inplace(ptr(w), n, ptr(self._reduce_ws), ptr(stats), stream_ptr()),
+                   "tb_normalize_inplace")
+        h = stats.cpu().numpy()
+        return float(h[0]), float(h[1])
+
+    def g_hist(self, w: torch.Tensor, n: int):
+        cnt = self.ws.i64("trim_cnt", 2048)
+        s1 = self.ws.f64("trim_s1", 2048)
+        s2 = self.ws.f64("trim_s2", 2048)
+        _lib.check(self.lib.tb_binade_hist(ptr(w), n, ptr(cnt), ptr(s1), ptr(s2), stream_ptr()), "tb_binade_hist")
+        return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
+
+    def g_sum3(self, vals: torch.Tensor, m: int, thr: float):
+        """(count, sum w, sum w^2) over w >= thr."""
+        out3 = self.ws.f64("trim_m3", 3)
+        if m > 0:
+            _lib.check(self.lib.tb_masked_sums(ptr(vals), m, float(thr), ptr(self._reduce_ws), ptr(out3),
+                                               stream_ptr()), "tb_masked_sums")
+        else:
+            out3.zero_()
+        c, a1, a2 = out3.cpu().numpy()
+        return float(c), float(a1), float(a2)
+
+    def g_select(self, base, rows, stride: int, m: int, ncols: int, mult, ranks: torch.Tensor, nranks: int,
+                 out: torch.Tensor) -> torch.Tensor:
+        sws = self.ws.bytes("select", self.lib.tb_select_workspace_bytes(ncols, nranks))
+        _lib.check(self.lib.tb_select_ranks(ptr(base), ptr(rows), stride, m, ncols, ptr(mult), ptr(ranks), nranks,
+                                            ptr(sws), ptr(out), stream_ptr()), "tb_select_ranks")
+        return out
+
     # -- trim_weights (tools.py:10-55) ------------------------------------------------------
     def trim(self, w: torch.Tensor, n: int, ess: float = TRIM_ESS, bins: int = TRIM_BINS):
         """Normalises ``w`` IN PLACE (tools.py:36) and returns (idx int64[n_trim], w_trim[n_trim]).
@@ -226,20 +264,14 @@ class Kernels:
         stopping at the first i whose trimmed ESS ratio reaches ``ess``.  The ratio is monotone in
         the threshold, so the same i is found by (1) one binade histogram pass that brackets the
         flip, (2) exact evaluations (radix order statistics + masked sums) of the few percentile
-        grid points inside the bracket, by bisection."""
+        grid points inside the bracket, by bisection.  ``n`` is the LOCAL length; every count,
+        rank and sum below is global (the g_* hooks all-reduce when the ensemble is sharded)."""
         lib = self.lib
         st = stream_ptr()
-        stats = self.ws.f64("trim_stats", 3)
-        _lib.check(lib.tb_normalize_inplace(ptr(w), n, ptr(self._reduce_ws), ptr(stats), st), "tb_normalize_inplace")
-        cnt = self.ws.i64("trim_cnt", 2048)
-        s1 = self.ws.f64("trim_s1", 2048)
-        s2 = self.ws.f64("trim_s2", 2048)
-        _lib.check(lib.tb_binade_hist(ptr(w), n, ptr(cnt), ptr(s1), ptr(s2), st), "tb_binade_hist")
-        h_stats = stats.cpu().numpy()
-        h_cnt = cnt.cpu().numpy().astype(np.int64)
-        h_s1 = s1.cpu().numpy()
-        h_s2 = s2.cpu().numpy()
-        ess_total = 1.0 / h_stats[1]
+        _, sumsq = self.g_normalize(w, n)
+        h_cnt, h_s1, h_s2 = self.g_hist(w, n)
+        n_glob = self.g_int(n)
+        ess_total = 1.0 / sumsq
         # suffix sums over binades (threshold at the lower edge of binade b keeps bins >= b)
         s1_ge = np.cumsum(h_s1[::-1])[::-1]
         s2_ge = np.cumsum(h_s2[::-1])[::-1]
@@ -249,7 +281,7 @@ class Kernels:
         bstar = int(np.max(np.nonzero(ok_edge)[0]))          # highest binade edge that still passes
         cnt_lt = np.concatenate([[0], np.cumsum(h_cnt)])      # elements in bins < b
         percentiles = np.linspace(0, 99, bins)
-        pos = [percentile_position(n, float(p)) for p in percentiles]
+        pos = [percentile_position(n_glob, float(p)) for p in percentiles]
         lo_arr = np.array([p[0] for p in pos], dtype=np.int64)
         hi_arr = np.array([p[1] for p in pos], dtype=np.int64)
         bin_lo = np.searchsorted(cnt_lt, lo_arr, side="right") - 1
@@ -261,7 +293,7 @@ class Kernels:
         cand = np.union1d(amb, [best]).astype(np.int64)   # grid points that may need an exact evaluation
 
         cache = {}
-        comp = None  # (values tensor, count, n_below)
+        comp = None  # (values tensor, local count, global count below the compacted set)
 
         def exact(i: int):
             nonlocal comp
@@ -280,20 +312,16 @@ class Kernels:
                     _lib.check(lib.tb_compact_ge(ptr(w), n, edge, 1.0, ptr(cws), None, ptr(wc), ptr(nout), st),
                                "tb_compact_ge")
                     m = int(nout.item())
-                    comp = (wc, m, n - m)
+                    comp = (wc, m, n_glob - self.g_int(m))
             vals, m, below = comp
             lo, hi, g = pos[i]
             ranks = self.ws.i64("trim_ranks", 2)
             ranks.copy_(torch.tensor([lo - below, hi - below], dtype=torch.int64))
             sel = self.ws.f64("trim_sel", 2)
-            sws = self.ws.bytes("select", lib.tb_select_workspace_bytes(1, 2))
-            _lib.check(lib.tb_select_ranks(ptr(vals), None, 1, m, 1, None, ptr(ranks), 2, ptr(sws), ptr(sel), st),
-                       "tb_select_ranks")
+            self.g_select(vals, None, 1, m, 1, None, ranks, 2, sel)
             a, b = sel.cpu().numpy()
             thr = numpy_lerp(float(a), float(b), g)
-            out3 = self.ws.f64("trim_m3", 3)
-            _lib.check(lib.tb_masked_sums(ptr(vals), m, thr, ptr(self._reduce_ws), ptr(out3), st), "tb_masked_sums")
-            c, a1, a2 = out3.cpu().numpy()
+            c, a1, a2 = self.g_sum3(vals, m, thr)
             good = ((a1 * a1 / a2) / ess_total) >= ess
             cache[i] = (bool(good), thr)
             return cache[i]
@@ -309,17 +337,21 @@ class Kernels:
                 hi_i = mid - 1
         thr = exact(chosen)[1]
         # final: deterministic sum over the kept set on the full array, then ordered compaction
-        out3 = self.ws.f64("trim_m3", 3)
-        _lib.check(lib.tb_masked_sums(ptr(w), n, thr, ptr(self._reduce_ws), ptr(out3), st), "tb_masked_sums")
-        c, a1, _ = out3.cpu().numpy()
-        n_trim = int(c)
-        idx = torch.empty(n_trim, dtype=torch.int64, device=self.device)
-        wt = torch.empty(n_trim, dtype=F64, device=self.device)
+        c_glob, a1, _ = self.g_sum3(w, n, thr)
         nout = self.ws.i64("trim_nout", 1)
         cws = self.ws.bytes("compact", lib.tb_compact_workspace_bytes(n))
-        _lib.check(lib.tb_compact_ge(ptr(w), n, thr, float(a1), ptr(cws), ptr(idx), ptr(wt), ptr(nout), st),
-                   "tb_compact_ge")
-        self.last_trim = dict(bin=chosen, threshold=thr, n_trim=n_trim, n_exact=len(cache))
+        if self.sharded:     # local kept count differs from the global one
+            _lib.check(lib.tb_compact_ge(ptr(w), n, thr, float(a1), ptr(cws), None, None, ptr(nout), st),
+                       "tb_compact_ge")
+            n_loc = int(nout.item())
+        else:
+            n_loc = int(c_glob)
+        idx = torch.empty(n_loc, dtype=torch.int64, device=self.device)
+        wt = torch.empty(n_loc, dtype=F64, device=self.device)
+        if n_loc:
+            _lib.check(lib.tb_compact_ge(ptr(w), n, thr, float(a1), ptr(cws), ptr(idx), ptr(wt), ptr(nout), st),
+                       "tb_compact_ge")
+        self.last_trim = dict(bin=chosen, threshold=thr, n_trim=int(c_glob), n_exact=len(cache))
         return idx, wt
 
 
@@ -369,7 +401,7 @@ class Reweighter:
         out = core.k.probe(ens, beta).cpu().numpy()
         ess = float(out[3])
         if core.warmup_regime and beta == 0.0:
-            ess = uniform_weights_ess(ens.n_total)
+            ess = uniform_weights_ess(ens.n_total_global)
         metric = ess
         if self.volume_variation is not None:
             w = core.k.weights(ens, beta, core.k.probe_out, core.weights_buffer())
@@ -439,7 +471,7 @@ class Reweighter:
         target = self.ess_ratio * n
         dynamic = self.volume_variation is not None
         k = core.k
-        if not dynamic and self.device_search:
+        if not dynamic and self.device_search and not k.sharded:
             beta, ess, stats = self._device_search(beta_prev, target)
         else:
             lo, hi = self._ess_bracket(beta_prev, target)
@@ -477,7 +509,7 @@ class Reweighter:
         if core.warmup_regime:
             # all stored generations are at beta = 0: every weight is exactly equal and the
             # `ESS <= target` branch depends on numpy's rounding
-            ess0 = uniform_weights_ess(ens.n_total)
+            ess0 = uniform_weights_ess(ens.n_total_global)
             self.probe_log.append((beta_prev, ess0))
             if ess0 <= target:
                 out = k.probe(ens, beta_prev)
@@ -510,32 +542,41 @@ class Trainer:
         st = stream_ptr()
         idx, wt = k.trim(weights, ens.n_total)
         core.trace["trim_idx"], core.trace["trim_w"] = idx, wt
-        n_trim = int(idx.numel())
+        n_trim = int(idx.numel())                       # local; equals the global count on one GPU
+        n_trim_glob = int(k.last_trim["n_trim"])
+        m_total = 4 * n_trim_glob
         # modes.py:266-275: renormalise, draw 4n rows with replacement
-        stats3 = k.ws.f64("train_stats", 3)
-        _lib.check(lib.tb_normalize_inplace(ptr(wt), n_trim, ptr(k._reduce_ws), ptr(stats3), st), "normalize")
-        cdf = k.cdf(wt, n_trim, "train_cdf")
-        m_total = 4 * n_trim
+        if n_trim or not k.sharded:
+            k.g_normalize(wt, n_trim)
+        elif k.sharded:
+            k.g_sum3(wt, 0, 0.0)                        # keep the collective sequence aligned across ranks
         draws = core.rng.train_u(m_total)
         didx = k.ws.i64("train_didx", m_total)
-        k.search_right(cdf, n_trim, draws, didx)
-        counts = k.ws.i32("train_counts", n_trim)
-        _lib.check(lib.tb_count_indices(ptr(didx), m_total, ptr(counts), n_trim, st), "tb_count_indices")
+        if k.sharded:
+            k.sharded_search(wt, max(n_trim, 1), draws, didx, "train_cdf")
+        else:
+            cdf = k.cdf(wt, n_trim, "train_cdf")
+            k.search_right(cdf, n_trim, draws, didx)
+        counts = k.ws.i32("train_counts", max(n_trim, 1))
+        _lib.check(lib.tb_count_indices(ptr(didx), m_total, ptr(counts), max(n_trim, 1), st), "tb_count_indices")
         core.trace["train_draw_idx"] = didx
         # student.py:62: per-dimension median of the 4n-row multiset (even count: mean of the middle pair)
         ranks = torch.tensor([m_total // 2 - 1, m_total // 2], dtype=torch.int64, device=core.device)
         pair = k.ws.f64("train_pair", 2 * d)
-        sws = k.ws.bytes("select", lib.tb_select_workspace_bytes(d, 2))
-        _lib.check(lib.tb_select_ranks(ptr(ens.u), ptr(idx), d, n_trim, d, ptr(counts), ptr(ranks), 2, ptr(sws),
-                                       ptr(pair), st), "tb_select_ranks")
+        k.g_select(ens.u, idx, d, n_trim, d, counts, ranks, 2, pair)
         mean = torch.empty((1, d), dtype=F64, device=core.device)
         _lib.check(lib.tb_median_pairs(ptr(pair), d, ptr(mean), st), "tb_median_pairs")
         # student.py:63: Sigma = cov(ddof=1)*(M-1)/M + diag(var)/M from count-weighted moments
         mws = k.ws.bytes("mom", lib.tb_moments_workspace_bytes(d))
         cmean = k.ws.f64("train_cmean", d)
         scatter = k.ws.f64("train_scatter", d * d)
-        _lib.check(lib.tb_counted_moments(ptr(ens.u), ptr(idx), ptr(counts), n_trim, d, 1.0 / m_total, ptr(mws),
-                                          ptr(cmean), ptr(scatter), st), "tb_counted_moments")
+        if k.sharded:
+            from .sharded import sharded_mode_moments
+
+            sharded_mode_moments(core, idx, counts, n_trim, m_total, cmean, scatter)
+        else:
+            _lib.check(lib.tb_counted_moments(ptr(ens.u), ptr(idx), ptr(counts), n_trim, d, 1.0 / m_total, ptr(mws),
+                                              ptr(cmean), ptr(scatter), st), "tb_counted_moments")
         cov = torch.empty((1, d, d), dtype=F64, device=core.device)
         _lib.check(lib.tb_student_sigma(ptr(scatter), d, float(m_total), ptr(cov), st), "tb_student_sigma")
         # student.py:75-79 + modes.py:105-119: Cholesky (regularise on failure), inverse.  The EM loop
@@ -557,12 +598,20 @@ class Resampler:
     def run(self, weights: Optional[torch.Tensor]) -> None:
         core = self.core
         st = core.state
-        n = core.config.n_particles
+        n = core.n_local
         if float(st.raw("beta")) == 0.0:               # resample.py:69-72
             st.set_current("assignments", np.zeros(n, dtype=int))
             return
         ens = core.ensemble
         k = core.k
+        if k.sharded:
+            if core.config.resample != "mult":
+                raise NotImplementedError("systematic resampling is not sharded yet; use resample='mult' on >1 GPU")
+            from .sharded import sharded_resample
+
+            u, logl = sharded_resample(core, weights, core.rng.resample_u(core.n_global))
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
+            return
         cdf = k.cdf(weights, ens.n_total)
         idx = k.ws.i64("res_idx", n)
         if core.config.resample == "mult":
@@ -589,7 +638,7 @@ class Mutator:
         core = self.core
         st = core.state
         cfg = core.config
-        n, d = cfg.n_particles, cfg.n_dim
+        n, d = core.n_local, cfg.n_dim
         k = core.k
         lib = k.lib
         sp = stream_ptr()
@@ -602,9 +651,15 @@ class Mutator:
             _lib.check(lib.tb_prior_draw(n, C.byref(params), ptr(tape_u), ptr(u), None, ptr(logl), sp),
                        "tb_prior_draw")
             st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int),
-                               "calls": st.raw("calls") + n, "steps": 1, "acceptance": 1.0, "efficiency": 1.0})
+                               "calls": st.raw("calls") + core.n_global, "steps": 1, "acceptance": 1.0,
+                               "efficiency": 1.0})
             bad = torch.isinf(logl)
-            if bool(bad.any()):                         # mutate.py:122-148 (rare; bookkeeping on device tensors)
+            any_bad = bool(bad.any())
+            if k.sharded:
+                any_bad = bool(k.g_int(int(any_bad)))
+                if any_bad:
+                    raise NotImplementedError("infinite log-likelihoods at warm-up are not handled on >1 GPU yet")
+            if any_bad:                                 # mutate.py:122-148 (rare; bookkeeping on device tensors)
                 every = torch.arange(n, device=core.device)
                 inf_idx, fin_idx = every[bad], every[~bad]
                 if fin_idx.numel() > 0:
@@ -627,7 +682,13 @@ class Mutator:
         n_cap = cfg.n_max_steps * d
         launched = 0
         budget = min(n_min, n_cap)
-        while True:
+        if k.sharded:
+            from .sharded import sharded_mcmc_loop
+
+            k.comm.allreduce_sum_(ctrl[8 + K: 8 + 2 * K])          # walkers per mode: global counts
+            h, launched = sharded_mcmc_loop(core, params, tape_ref, u, logl, qcur, ws, ctrl, min(n_min, n_cap),
+                                            n_cap, self.CHUNK)
+        while not k.sharded:
             if tape is not None:
                 budget = min(budget, tape.steps - launched)
             if budget > 0:
