@@ -160,6 +160,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- untimed library warm-up: one small complete run loads every kernel module (CUDA lazy loading),
+    #      sizes the NCCL channels and fills the allocator pools --------------------------------------------
+    ws_ = tp.Sampler(tp.UniformPrior(-10.0, 10.0, N_DIM), tp.Rosenbrock(N_DIM), N_DIM, n_particles=4096 * world,
+                     vectorize=True, clustering=False, random_state=1)
+    ws_.run(n_total=1024, progress=False)
+    del ws_
+    barrier()
+
     # ---- device-timed region: K PS iterations after W warm-up iterations ---------------------------
     s = new_sampler()
     core = s._core
@@ -214,13 +222,15 @@ def main():
 
     ens = core.ensemble
     reps = 20
+    from tempest_b200.steps import Kernels
+
     for _ in range(3):
-        core.k.probe(ens, 0.5)
+        Kernels.probe(core.k, ens, 0.5)            # the local kernel only (no cross-rank merge)
     torch.cuda.synchronize()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for i in range(reps):
-        core.k.probe(ens, 0.3 + 0.01 * i)
+        Kernels.probe(core.k, ens, 0.3 + 0.01 * i)
     p1.record()
     torch.cuda.synchronize()
     probe_ms = p0.elapsed_time(p1) / reps

@@ -229,10 +229,13 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
                   int32_t count, tb_stream_t stream);
 
 /* ---- entry points used when particles are sharded over GPUs ---------------------- */
-/* multinomial search inside a global cdf: this shard's cdf starts at `offset`, the global total is
- * `total`; idx = local ancestor index or -1 when the draw belongs to another shard */
-int tb_search_right_sharded(const double* cdf, int64_t n, double offset, double total, int32_t is_first,
-                            const double* draws, int64_t m, int64_t* idx, tb_stream_t stream);
+/* multinomial search inside the GLOBAL cdf (generation-major, rank-minor): this rank holds one
+ * segment per generation, seg_begin[n_seg+1] local positions; global value of local element j in
+ * segment s is cdf[j] + seg_shift[s]; seg_start[s] is the global cdf value just before segment s.
+ * idx = local ancestor index or -1 when the draw belongs to another rank. */
+int tb_search_right_sharded(const double* cdf, int64_t n, const int64_t* seg_begin, const double* seg_shift,
+                            const double* seg_start, int32_t n_seg, double total, const double* draws,
+                            int64_t m, int64_t* idx, tb_stream_t stream);
 /* w /= denom */
 int tb_scale_inplace(double* w, int64_t n, double denom, tb_stream_t stream);
 /* one stage of tb_select_ranks: 0 init, 1 local histogram of `level`, 2 pick from the (all-reduced)

@@ -77,7 +77,7 @@ SIGNATURES = {
                               PTR, PTR, c_i32, PTR]),
     "tb_philox_uniform": (c_i32, [c_u64, c_u64, c_u32, c_i64, c_i64, PTR, PTR]),
     "tb_set_mcmc_generic": (c_i32, [c_i32]),
-    "tb_search_right_sharded": (c_i32, [PTR, c_i64, c_f64, c_f64, c_i32, PTR, c_i64, PTR, PTR]),
+    "tb_search_right_sharded": (c_i32, [PTR, c_i64, PTR, PTR, PTR, c_i32, c_f64, PTR, c_i64, PTR, PTR]),
     "tb_scale_inplace": (c_i32, [PTR, c_i64, c_f64, PTR]),
     "tb_select_stage": (c_i32, [PTR, PTR, c_i64, c_i64, c_i32, PTR, PTR, c_i32, PTR, PTR, c_i32, c_i32, PTR]),
     "tb_select_hist_offset": (SIZE, [c_i32, c_i32]),

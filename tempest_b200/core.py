@@ -93,6 +93,11 @@ class SamplerCore:
     def warmup_regime(self) -> bool:
         return self.ensemble.all_warmup()
 
+    def generation_bounds(self) -> torch.Tensor:
+        """Local start positions [T+1] of every stored generation in this rank's history shard."""
+        b = np.concatenate([[0], np.cumsum(self.ensemble.gen_n_local)]).astype(np.int64)
+        return torch.as_tensor(b).to(self.device)
+
     def weights_buffer(self) -> torch.Tensor:
         n = self.ensemble.n_total
         if self._weights is None or self._weights.numel() < n:

@@ -348,21 +348,36 @@ search_right_kernel(const double* __restrict__ cdf, int64_t n, const double* __r
   }
 }
 
-// sharded multinomial search: this shard's cdf is offset by `offset` inside a global cdf of total
-// `total`; idx = local ancestor index, or -1 when the draw belongs to another shard.
+// Sharded multinomial search.  The global cdf runs over generations, and inside a generation over
+// ranks; this rank holds one contiguous SEGMENT per generation.  cdf[] is the rank-local cumulative
+// sum; global value of local element j in segment s:  g(j) = cdf[j] + seg_shift[s]  (seg_shift folds
+// "global offset of the segment" minus "local sum before it").  idx = local ancestor index, or -1
+// when the draw's ancestor lives on another rank (seg_start[s] = global cdf value just before
+// segment s decides ownership of a segment's first element).
+__device__ __forceinline__ int seg_of(const int64_t* __restrict__ seg_begin, int S, int64_t j) {
+  int lo = 0, hi = S;                  // last s with seg_begin[s] <= j
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (__ldg(seg_begin + mid) <= j) lo = mid; else hi = mid; }
+  return lo;
+}
+
 __global__ void __launch_bounds__(kBlock)
-search_right_sharded_kernel(const double* __restrict__ cdf, int64_t n, double offset, double total, int is_first,
-                            const double* __restrict__ draws, int64_t m, int64_t* __restrict__ idx) {
-  const double lo_edge = __ddiv_rn(offset, total);
+search_right_sharded_kernel(const double* __restrict__ cdf, int64_t n, const int64_t* __restrict__ seg_begin,
+                            const double* __restrict__ seg_shift, const double* __restrict__ seg_start, int S,
+                            double total, const double* __restrict__ draws, int64_t m, int64_t* __restrict__ idx) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
     const double u = __ldg(draws + k);
     int64_t lo = 0, hi = n;
     while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if (__ddiv_rn(__dadd_rn(offset, __ldg(cdf + mid)), total) <= u) lo = mid + 1; else hi = mid;
+      const int64_t mid = (lo + hi) >> 1;
+      const int s = seg_of(seg_begin, S, mid);
+      if (__ddiv_rn(__dadd_rn(__ldg(cdf + mid), __ldg(seg_shift + s)), total) <= u) lo = mid + 1; else hi = mid;
     }
-    const bool mine = (lo < n) && (is_first || lo_edge <= u);
+    bool mine = lo < n;
+    if (mine) {
+      const int s = seg_of(seg_begin, S, lo);
+      if (lo == __ldg(seg_begin + s)) mine = __ddiv_rn(__ldg(seg_start + s), total) <= u;
+    }
     idx[k] = mine ? lo : -1;
   }
 }
@@ -440,12 +455,14 @@ int tb_search_right(const double* cdf, int64_t n, const double* draws, int64_t m
   return TB_OK;
 }
 
-int tb_search_right_sharded(const double* cdf, int64_t n, double offset, double total, int32_t is_first,
-                            const double* draws, int64_t m, int64_t* idx, tb_stream_t stream) {
-  if (n <= 0 || m < 0 || !cdf || (m > 0 && (!draws || !idx))) return TB_ERR_ARG;
+int tb_search_right_sharded(const double* cdf, int64_t n, const int64_t* seg_begin, const double* seg_shift,
+                            const double* seg_start, int32_t n_seg, double total, const double* draws, int64_t m,
+                            int64_t* idx, tb_stream_t stream) {
+  if (n <= 0 || m < 0 || n_seg <= 0 || !cdf || !seg_begin || !seg_shift || !seg_start || (m > 0 && (!draws || !idx)))
+    return TB_ERR_ARG;
   if (m == 0) return TB_OK;
-  search_right_sharded_kernel<<<stream_grid(m, kBlock, 16), kBlock, 0, as_stream(stream)>>>(cdf, n, offset, total,
-                                                                                          is_first, draws, m, idx);
+  search_right_sharded_kernel<<<stream_grid(m, kBlock, 16), kBlock, 0, as_stream(stream)>>>(
+      cdf, n, seg_begin, seg_shift, seg_start, n_seg, total, draws, m, idx);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

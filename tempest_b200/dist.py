@@ -37,9 +37,10 @@ class Comm:
         """[world, *t.shape] in rank order."""
         if not self.on:
             return t.unsqueeze(0)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        flat = t.contiguous().reshape(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.reshape((self.world,) + tuple(t.shape))
 
     def allgather_rows(self, t: torch.Tensor) -> torch.Tensor:
         """Concatenate variable-length first dimensions in rank order (padded all-gather)."""

@@ -119,24 +119,37 @@ class ShardedKernels(Kernels):
         return 0.5 * math.sqrt(float(raw.item()))
 
     # -- global multinomial draws over the sharded cdf ---------------------------------------------------
-    def sharded_search(self, p: torch.Tensor, n: int, draws: torch.Tensor, out: torch.Tensor, name: str):
-        """Ancestor index of every (replicated) draw that falls in this rank's part of the global
-        cdf (rank-major concatenation), -1 elsewhere.  Returns (out, global total)."""
+    def sharded_search(self, p: torch.Tensor, n: int, seg_begin: torch.Tensor, draws: torch.Tensor,
+                       out: torch.Tensor, name: str):
+        """Ancestor index of every (replicated) draw whose ancestor lives on this rank, -1 elsewhere.
+
+        The global cdf is ordered like the single-GPU ensemble (generation-major, then slot), so the
+        same draws select the same ancestors for any number of GPUs.  ``seg_begin`` [S+1] are the local
+        start positions of this rank's per-generation segments (may be empty)."""
+        S = int(seg_begin.numel()) - 1
         if n > 0 and p.numel() > 0:
             cdf = self.cdf(p, n, name)
-            last = cdf[n - 1: n].clone()
-        else:                                   # this rank holds none of the candidates
-            n, cdf, last = 0, None, torch.zeros(1, dtype=F64, device=self.device)
-        totals = self.comm.allgather(last).flatten().cpu().numpy()
-        offset = float(np.sum(totals[: self.comm.rank])) if self.comm.rank else 0.0
-        total = float(np.sum(totals))
+            csum = torch.cat([torch.zeros(1, dtype=F64, device=self.device), cdf])   # csum[j] = sum of p[:j]
+            before = csum[seg_begin[:-1]]                                           # local sum before each segment
+            seg_tot = csum[seg_begin[1:]] - before
+        else:
+            n, cdf = 0, None
+            before = torch.zeros(S, dtype=F64, device=self.device)
+            seg_tot = torch.zeros(S, dtype=F64, device=self.device)
+        tot = self.comm.allgather(seg_tot).cpu().numpy()          # [G, S]
+        # running sum in global order: generation-major, rank-minor (identical on every rank)
+        flat = tot.T.reshape(-1)
+        goff = np.concatenate([[0.0], np.cumsum(flat)])
+        total = float(goff[-1])
+        start = goff[:-1].reshape(S, self.comm.world)[:, self.comm.rank].copy()      # global value before my segment
         if n == 0:
             out.fill_(-1)
             return out, total
-        # "first" = first rank with a non-empty share (its lower edge is 0 by construction)
-        first = int(not np.any(totals[: self.comm.rank] > 0))
-        _lib.check(self.lib.tb_search_right_sharded(ptr(cdf), n, offset, total, first, ptr(draws),
-                                                    draws.numel(), ptr(out), stream_ptr()), "tb_search_right_sharded")
+        seg_start = torch.as_tensor(start, dtype=F64).to(self.device)
+        seg_shift = seg_start - before
+        _lib.check(self.lib.tb_search_right_sharded(ptr(cdf), n, ptr(seg_begin), ptr(seg_shift), ptr(seg_start), S,
+                                                    total, ptr(draws), draws.numel(), ptr(out), stream_ptr()),
+                   "tb_search_right_sharded")
         return out, total
 
 
@@ -165,7 +178,7 @@ def sharded_resample(core, weights: torch.Tensor, draws: torch.Tensor):
     n_glob = core.n_global
     d = ens.n_dim
     idx = k.ws.i64("res_idx", n_glob)
-    k.sharded_search(weights, ens.n_total, draws, idx, "cdf")
+    k.sharded_search(weights, ens.n_total, core.generation_bounds(), draws, idx, "cdf")
     own = torch.nonzero(idx >= 0).flatten()
     rows = torch.empty((own.numel(), d + 1), dtype=F64, device=core.device)
     if own.numel():

@@ -197,7 +197,7 @@ class Kernels:
         out = self.ws.f64("vv_out", 2)
         _lib.check(self.lib.tb_mahalanobis_cv(ptr(u), ptr(w), n, d, ptr(mean), ptr(inv), ptr(self._reduce_ws),
                                               ptr(out), stream_ptr()), "tb_mahalanobis_cv")
-        return float(out.item())
+        return float(out[0].item())
 
     # -- resampling -----------------------------------------------------------------------
     def cdf(self, p: torch.Tensor, n: int, name: str = "cdf") -> torch.Tensor:
@@ -553,7 +553,9 @@ class Trainer:
         draws = core.rng.train_u(m_total)
         didx = k.ws.i64("train_didx", m_total)
         if k.sharded:
-            k.sharded_search(wt, max(n_trim, 1), draws, didx, "train_cdf")
+            # segments of the trimmed set per generation (trim indices are ascending = generation-major)
+            seg_begin = torch.searchsorted(idx, core.generation_bounds())
+            k.sharded_search(wt, n_trim, seg_begin, draws, didx, "train_cdf")
         else:
             cdf = k.cdf(wt, n_trim, "train_cdf")
             k.search_right(cdf, n_trim, draws, didx)

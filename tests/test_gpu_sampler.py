@@ -142,6 +142,21 @@ def test_generic_step_kernel_matches_oracle_on_tapes():
     np.testing.assert_allclose(s.state.get_history("logl"), np.array(o.hist["logl"]), rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_run_matches_single_gpu():
+    """Sharded over 2 ranks (NCCL) the run must reproduce the 1-GPU beta sequence, step counts and logZ."""
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(ROOT, "tools", "dist_check.py"), "4096"],
+                         capture_output=True, text=True, timeout=600)
+    assert "DIST OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_host_driven_search_equals_device_search():
     import tempest_b200 as tp
 
