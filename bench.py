@@ -151,9 +151,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_particles = args.particles
 
+    stage_acc = {}
+
     def new_sampler():
-        return tp.Sampler(tp.UniformPrior(-10.0, 10.0, N_DIM), tp.Rosenbrock(N_DIM), N_DIM,
-                          n_particles=n_particles, vectorize=True, clustering=False, random_state=SEED)
+        smp = tp.Sampler(tp.UniformPrior(-10.0, 10.0, N_DIM), tp.Rosenbrock(N_DIM), N_DIM,
+                         n_particles=n_particles, vectorize=True, clustering=False, random_state=SEED)
+        smp._core.stage_ms = stage_acc
+        return smp
 
     def barrier():
         if world > 1:
@@ -214,52 +218,69 @@ def main():
     clock_info = clocks.stop()
     it_s = args.steps / (ms * 1e-3)
     evals_s = calls_acc / (ms * 1e-3)
-    stage_ms = dict(getattr(core, "stage_ms", {}))
-    n_hist = core.ensemble.n_total
-
-    # ---- roofline of the dominant HBM kernel: the ESS probe (16 B / particle) ---------------------------
-    from tempest_b200.ensemble import ptr, stream_ptr
-
-    ens = core.ensemble
-    reps = 20
-    from tempest_b200.steps import Kernels
-
-    for _ in range(3):
-        Kernels.probe(core.k, ens, 0.5)            # the local kernel only (no cross-rank merge)
-    torch.cuda.synchronize()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for i in range(reps):
-        Kernels.probe(core.k, ens, 0.3 + 0.01 * i)
-    p1.record()
-    torch.cuda.synchronize()
-    probe_ms = p0.elapsed_time(p1) / reps
-    peak, peak_src = peak_hbm_gbs()
-    achieved = 16.0 * n_hist / (probe_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "probe_kernel / next_beta_kernel (tb_reweight.cu)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "algorithmic_bytes_per_particle": 16, "particles": n_hist, "launch_ms": probe_ms,
-                "peak_source": peak_src}
+    stage_ms = dict(stage_acc)
 
     # ---- end to end through the public API (host in, host out) -----------------------------------------
-    e2e = None
-    if rank == 0 or world > 1:
-        barrier()
-        t0 = time.perf_counter()
-        s2 = new_sampler()
-        s2.run(n_total=4096, progress=False)
-        logz, _ = s2.evidence()
-        x, w, l = s2.posterior()
+    barrier()
+    t0 = time.perf_counter()
+    s2 = new_sampler()
+    s2.run(n_total=4096, progress=False)
+    logz, _ = s2.evidence()
+    x, w, l = s2.posterior()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    T2 = s2.state.get_history_length()
+    d2h = (x.nbytes + w.nbytes + l.nbytes) / T2 + 16 * 8 * 12 + 3 * 2048 * 8
+    h2d = 3 * T2 * 8 + 64
+    e2e = {"value": T2 / dt, "unit": "PS iterations/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "iterations": T2, "seconds": dt, "logz": float(logz),
+           "logl_evals_per_s": s2.state.get_current("calls") / dt, "posterior_samples": int(x.shape[0]),
+           "note": "Sampler(...).run(4096) + evidence() + posterior() to host numpy; inputs are the problem "
+                   "definition (parameters), outputs the weighted posterior sample"}
+    del x, w, l
+
+    # ---- roofline of the HBM-bound hot kernel, measured live on the FULL persistent ensemble of that run:
+    #      the ESS probe streams logl[] and C[] once = 16 algorithmic bytes per stored particle ---------------
+    from tempest_b200.steps import Kernels
+
+    core2 = s2._core
+    ens = core2.ensemble
+    n_hist = ens.n_total
+
+    def cuda_ms(fn, reps=20):
+        for _ in range(3):
+            fn()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        T2 = s2.state.get_history_length()
-        d2h = (x.nbytes + w.nbytes + l.nbytes) / T2 + 16 * 8 * 12 + 3 * 2048 * 8
-        h2d = 3 * T2 * 8 + 64
-        e2e = {"value": T2 / dt, "unit": "PS iterations/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "iterations": T2, "seconds": dt, "logz": float(logz),
-               "logl_evals_per_s": s2.state.get_current("calls") / dt, "posterior_samples": int(x.shape[0]),
-               "note": "Sampler(...).run(4096) + evidence() + posterior() to host numpy; inputs are the problem "
-                       "definition (parameters), outputs the weighted posterior sample"}
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    peak, peak_src = peak_hbm_gbs()
+    probe_ms = cuda_ms(lambda i=0: Kernels.probe(core2.k, ens, 0.3 + 0.01 * i))     # local kernel only
+    achieved = 16.0 * n_hist / (probe_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "probe_kernel (tb_reweight.cu; same loop as next_beta_kernel)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_particle": 16, "particles": n_hist, "launch_ms": probe_ms,
+                "peak_source": peak_src}
+    wbuf = core2.weights_buffer()
+    Kernels.probe(core2.k, ens, 1.0)
+    others = {}
+    ms_w = cuda_ms(lambda i=0: core2.k.weights(ens, 1.0, core2.k.probe_out, wbuf))
+    others["weights_kernel"] = {"ms": ms_w, "bytes_per_particle": 24, "gbs": 24.0 * n_hist / ms_w / 1e6}
+    ms_c = cuda_ms(lambda i=0: core2.k.cdf(wbuf, n_hist), reps=10)
+    others["cdf_exact (6 kernels)"] = {"ms": ms_c, "bytes_per_particle": 32, "gbs": 32.0 * n_hist / ms_c / 1e6}
+    if world == 1:
+        ms_n = cuda_ms(lambda i=0: core2.k.next_beta(ens, 0.5, 2.0 * n_particles, 0), reps=5)
+        npr = float(core2.k.ws.f64("nb_res", 16)[6].item())
+        others["next_beta_kernel"] = {"ms": ms_n, "probes": npr, "bytes_per_particle": 16 * npr,
+                                      "gbs": 16.0 * npr * n_hist / ms_n / 1e6}
+    for v in others.values():
+        v["frac"] = v["gbs"] / peak
+    roofline["other_kernels"] = others
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------------------
     cpu = None

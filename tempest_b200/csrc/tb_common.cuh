@@ -120,7 +120,7 @@ struct Ess3 {
   __device__ __forceinline__ void push(double a) {
     if (a <= m) {
       double d = a - m;
-      if (d > -746.0) {  // exp underflows to exactly 0 below -745.14
+      if (d > -40.0) {   // bitwise neutral: s1, s2 >= 1 (the maximum's own term), and e^-40 < 2^-53 cannot change them
         double w = exp(d);
         s1 += w;
         s2 += w * w;

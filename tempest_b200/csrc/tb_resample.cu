@@ -26,8 +26,8 @@
 namespace {
 using namespace tb;
 
-constexpr int kTile = 512;        // elements per tile
-constexpr int kTileThreads = 128; // 4 elements per thread
+constexpr int kTile = 2048;       // elements per tile
+constexpr int kTileThreads = 256; // 8 elements per thread
 constexpr int kHard = INT32_MIN;  // tile_E marker
 constexpr int kMinE = -960;       // below this the power-of-two scale factors leave the normal range
 
