@@ -26,8 +26,8 @@
 namespace {
 using namespace tb;
 
-constexpr int kTile = 2048;       // elements per tile
-constexpr int kTileThreads = 256; // 8 elements per thread
+constexpr int kTile = 1024;       // elements per tile
+constexpr int kTileThreads = 256; // 4 elements per thread
 constexpr int kHard = INT32_MIN;  // tile_E marker
 constexpr int kMinE = -960;       // below this the power-of-two scale factors leave the normal range
 
@@ -220,24 +220,32 @@ __device__ __forceinline__ long long warp_incl_scan_ll(long long v, int lane) {
 }
 
 // process elements [beg,end) literally or by validated 32-wide integer sub-tiles; writes cdf
+// The span is staged through shared memory in chunks (independent, fully pipelined loads) so the
+// serial sub-tile loop below never waits on HBM latency.
+constexpr int kStage = 2048;
 __device__ void hard_span(const double* __restrict__ p, double* __restrict__ cdf, int64_t beg, int64_t end,
-                          double& s, bool& have, int lane) {
-  for (int64_t b = beg; b < end; b += 32) {
+                          double& s, bool& have, int lane, double* stage) {
+ for (int64_t c0 = beg; c0 < end; c0 += kStage) {
+  const int64_t c1 = (c0 + kStage < end) ? c0 + kStage : end;
+  __syncwarp();
+  for (int64_t i = c0 + lane; i < c1; i += 32) stage[i - c0] = __ldg(p + i);
+  __syncwarp();
+  for (int64_t b = c0; b < c1; b += 32) {
     const int64_t i = b + lane;
-    const double v = (i < end) ? p[i] : 0.0;
+    const double v = (i < c1) ? stage[i - c0] : 0.0;
     bool ok = false;
     if (have && s >= 2.2250738585072014e-308) {
       const int E = exponent_of(s);
       if (E >= kMinE && E <= 1000) {
         const double up = pow2(52 - E), top = pow2(E + 1), q = pow2(E - 52);
-        long long inc = (i < end) ? inc_of(v, up, top) : 0;
+        long long inc = (i < c1) ? inc_of(v, up, top) : 0;
         const bool bad = __any_sync(0xffffffffu, inc < 0);
         if (!bad) {
           const long long incl = warp_incl_scan_ll(inc, lane);
           const long long S0 = __double2ll_rn(s * up);
           const long long tot = __shfl_sync(0xffffffffu, incl, 31);
           if (S0 + tot < (1LL << 53)) {
-            if (i < end) cdf[i] = (double)(S0 + incl) * q;
+            if (i < c1) cdf[i] = (double)(S0 + incl) * q;
             s = (double)(S0 + tot) * q;
             ok = true;
           }
@@ -245,19 +253,23 @@ __device__ void hard_span(const double* __restrict__ p, double* __restrict__ cdf
       }
     }
     if (!ok) {  // literal sequential adds (binade crossing, tie, leading zeros, tiny sums)
+      double mine = 0.0;
       for (int k = 0; k < 32; ++k) {
         const double vk = __shfl_sync(0xffffffffu, v, k);
-        if (b + k < end) {
+        if (b + k < c1) {
           if (!have) { s = vk; have = true; } else s = __dadd_rn(s, vk);
-          if (lane == k) cdf[b + k] = s;
+          if (lane == k) mine = s;
         }
       }
+      if (i < c1) cdf[i] = mine;
     }
   }
+ }
 }
 
 __global__ void __launch_bounds__(32)
 cdf_walk_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ cdf, CdfWs w, int64_t nt) {
+  __shared__ double stage[kStage];
   const int lane = threadIdx.x;
   double s = 0.0;
   bool have = false;   // numpy: cdf_0 = p_0 (no 0 + p_0)
@@ -266,7 +278,7 @@ cdf_walk_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ cd
     const int E = w.tile_E[t];
     if (E == kHard) {
       const int64_t beg = t * kTile, end = (beg + kTile < n) ? beg + kTile : n;
-      hard_span(p, cdf, beg, end, s, have, lane);
+      hard_span(p, cdf, beg, end, s, have, lane, stage);
       ++t;
       continue;
     }
@@ -288,7 +300,7 @@ cdf_walk_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ cd
     for (int64_t c = t + lane; c < t1; c += 32) w.tile_E[c] = kHard;
     __syncwarp();
     const int64_t beg = t * kTile, end = (t1 * kTile < n) ? t1 * kTile : n;
-    hard_span(p, cdf, beg, end, s, have, lane);
+    hard_span(p, cdf, beg, end, s, have, lane, stage);
     t = t1;
   }
 }
