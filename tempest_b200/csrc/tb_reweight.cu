@@ -42,33 +42,84 @@ struct ProbeWs {            // workspace layout (device)
   double partial[2][kMaxPartials][4];  // double-buffered {m, S1, S2, n_nonfinite}
 };
 
+// exp(d) for d in (-40, 0]: Cody-Waite reduction by ln2, degree-13 Taylor polynomial on |r| <= ln2/2
+// (remainder < 5e-18), scaled by 2^k through the exponent field (k >= -58, no denormals).  <= 1 ulp of
+// libdevice's exp on this range at roughly half its instruction count (no special-case handling).
+__constant__ double kExpC[18] = {
+    6755399441055744.0, 1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    1.6059043836821613e-10, 2.08767569878680989792e-09, 2.50521083854417187751e-08, 2.75573192239858906526e-07,
+    2.75573192239858906526e-06, 2.48015873015873015873e-05, 1.98412698412698412698e-04, 1.38888888888888888889e-03,
+    8.33333333333333333333e-03, 4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5, 1.0, -40.0};
+// (coefficients live in the constant bank so every DFMA takes its constant as an operand instead of
+// materialising a 64-bit immediate with two extra moves)
+__device__ __forceinline__ double exp_neg40(double d) {
+  const double t = fma(d, kExpC[1], kExpC[0]);                     // 1.5 * 2^52: round-to-nearest-integer trick
+  const double kf = t - kExpC[0];
+  const int k = __double2loint(t);                                 // low word of t holds the integer
+  double r = fma(kf, kExpC[2], d);
+  r = fma(kf, kExpC[3], r);
+  double p = kExpC[4];                                             // 1/13!
+#pragma unroll
+  for (int i = 5; i <= 15; ++i) p = fma(p, r, kExpC[i]);
+  p = fma(p, r, kExpC[16]);
+  p = fma(p, r, kExpC[16]);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// Streams (logl, C) once.  Four particles per iteration share one running-max update (rare), then
+// each contributes exp(a - m) unless it is below e^-40 (cannot move sums that contain the 1.0 of the
+// maximum).  `chk` turns NaN as soon as any a is non-finite (a * 0).
+__device__ __forceinline__ void probe4(Ess3& e, double& chk, double a0, double a1, double a2, double a3) {
+  chk = fma(a0, 0.0, chk); chk = fma(a1, 0.0, chk); chk = fma(a2, 0.0, chk); chk = fma(a3, 0.0, chk);
+  const double mx = fmax(fmax(a0, a1), fmax(a2, a3));
+  if (mx > e.m) {
+    const double r = (e.m == -INFINITY) ? 0.0 : exp(e.m - mx);
+    e.s1 *= r;
+    e.s2 *= r * r;
+    e.m = mx;
+  }
+  const double d0 = a0 - e.m, d1 = a1 - e.m, d2 = a2 - e.m, d3 = a3 - e.m;
+  if (d0 > -40.0) { const double w = exp_neg40(d0); e.s1 += w; e.s2 = fma(w, w, e.s2); }
+  if (d1 > -40.0) { const double w = exp_neg40(d1); e.s1 += w; e.s2 = fma(w, w, e.s2); }
+  if (d2 > -40.0) { const double w = exp_neg40(d2); e.s1 += w; e.s2 = fma(w, w, e.s2); }
+  if (d3 > -40.0) { const double w = exp_neg40(d3); e.s1 += w; e.s2 = fma(w, w, e.s2); }
+}
+
+__device__ __forceinline__ void probe1(Ess3& e, double& chk, double a) {
+  chk = fma(a, 0.0, chk);
+  if (a > e.m) {
+    const double r = (e.m == -INFINITY) ? 0.0 : exp(e.m - a);
+    e.s1 *= r;
+    e.s2 *= r * r;
+    e.m = a;
+  }
+  const double d = a - e.m;
+  if (d > -40.0) { const double w = exp_neg40(d); e.s1 += w; e.s2 = fma(w, w, e.s2); }
+}
+
 __device__ __forceinline__ void probe_slice(const double* __restrict__ logl, const double* __restrict__ C,
                                             int64_t n, double beta, Ess3& e, double& bad) {
-  // vectorised 2 x fp64 loads, 4 independent loads in flight per thread
+  // vectorised 2 x fp64 loads, 4 independent 16-byte loads in flight per thread
   const int64_t n2 = n >> 1;
   const double2* l2 = reinterpret_cast<const double2*>(logl);
   const double2* c2 = reinterpret_cast<const double2*>(C);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double chk = 0.0;
   for (; i + stride < n2; i += 2 * stride) {
-    double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
-    double2 lb = __ldg(l2 + i + stride), cb = __ldg(c2 + i + stride);
-    double a0 = __dsub_rn(__dmul_rn(la.x, beta), ca.x), a1 = __dsub_rn(__dmul_rn(la.y, beta), ca.y);
-    double a2 = __dsub_rn(__dmul_rn(lb.x, beta), cb.x), a3 = __dsub_rn(__dmul_rn(lb.y, beta), cb.y);
-    bad += (double)(!isfinite(a0)) + (double)(!isfinite(a1)) + (double)(!isfinite(a2)) + (double)(!isfinite(a3));
-    e.push(a0); e.push(a1); e.push(a2); e.push(a3);
+    const double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
+    const double2 lb = __ldg(l2 + i + stride), cb = __ldg(c2 + i + stride);
+    probe4(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x), __dsub_rn(__dmul_rn(la.y, beta), ca.y),
+           __dsub_rn(__dmul_rn(lb.x, beta), cb.x), __dsub_rn(__dmul_rn(lb.y, beta), cb.y));
   }
   for (; i < n2; i += stride) {
-    double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
-    double a0 = __dsub_rn(__dmul_rn(la.x, beta), ca.x), a1 = __dsub_rn(__dmul_rn(la.y, beta), ca.y);
-    bad += (double)(!isfinite(a0)) + (double)(!isfinite(a1));
-    e.push(a0); e.push(a1);
+    const double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
+    probe1(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x));
+    probe1(e, chk, __dsub_rn(__dmul_rn(la.y, beta), ca.y));
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    double a0 = __dsub_rn(__dmul_rn(logl[n - 1], beta), C[n - 1]);
-    bad += (double)(!isfinite(a0));
-    e.push(a0);
-  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+    probe1(e, chk, __dsub_rn(__dmul_rn(logl[n - 1], beta), C[n - 1]));
+  if (chk != chk) bad += 1.0;      // some a_s was NaN or +-inf (reported as a non-zero count)
 }
 
 // merge `nb` published partials in a fixed order; result identical in every caller
@@ -92,7 +143,7 @@ __device__ __forceinline__ void write_probe_result(double* out, const Ess3& e, d
   out[5] = bad;
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 5)
 probe_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n, double beta,
              ProbeWs* ws, double* __restrict__ out) {
   __shared__ double smem[160];
@@ -141,7 +192,7 @@ constexpr double kBetaTol = 1e-4, kBetaRtol = 1e-8, kEssTol = 0.01, kMetricAtol 
 constexpr int kMaxBisect = 200;                                                          // reweight.py:121
 constexpr double kTiny = 2.2250738585072014e-308;
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 5)
 next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n,
                  double beta_prev, double target, int flags, ProbeWs* ws, double* __restrict__ result,
                  double* __restrict__ plog, int plog_cap) {
@@ -247,7 +298,7 @@ int tb_probe(const double* logl, const double* C, int64_t n, double beta, void* 
              tb_stream_t stream) {
   if (n <= 0 || !logl || !C || !workspace || !out6) return TB_ERR_ARG;
   // 2 particles per thread per load; 4 CTAs of 256 threads per SM keep >= 32 x 16 B loads in flight per SM
-  int grid = stream_grid(n, kBlock * 4, 4);
+  int grid = stream_grid(n, kBlock * 4, 5);
   probe_kernel<<<grid, kBlock, 0, as_stream(stream)>>>(logl, C, n, beta, (ProbeWs*)workspace, out6);
   TB_CHECK_LAUNCH();
   return TB_OK;
@@ -280,7 +331,7 @@ int tb_next_beta(const double* logl, const double* C, int64_t n, double beta_pre
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, next_beta_kernel, kBlock, 0);
     if (e != cudaSuccess) return (int)e;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 5) per_sm = 5;
     if (per_sm < 1) return TB_ERR_UNSUPPORTED;
     max_coresident = per_sm * tb::sm_count();
     if (max_coresident > kMaxPartials) max_coresident = kMaxPartials;
