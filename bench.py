@@ -266,6 +266,12 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_particle": 16, "particles": n_hist, "launch_ms": probe_ms,
                 "peak_source": peak_src}
+    prof = os.path.join(ROOT, "profiles", "r01_probe.json")
+    if os.path.exists(prof):      # dram bytes per particle from the committed `ncu --set full` capture, scaled to this N_total
+        pj = json.load(open(prof))
+        roofline["traffic"] = pj["traffic_bytes_per_particle"] * n_hist
+        roofline["traffic_source"] = (f"{pj['source']}: dram read+write {pj['dram_bytes_read'] + pj['dram_bytes_write']} B "
+                                      f"at N_total={pj['n_total']} (algorithmic {pj['algorithmic_bytes']} B), scaled by N_total")
     wbuf = core2.weights_buffer()
     Kernels.probe(core2.k, ens, 1.0)
     others = {}

@@ -163,6 +163,15 @@ int tb_select_ranks(const double* base, const int64_t* rows, int64_t stride, int
                     int32_t ncols, const int32_t* mult, const int64_t* ranks, int32_t nranks,
                     void* workspace, double* out /*[ncols*nranks]*/, tb_stream_t stream);
 
+/* the adjacent pair of order statistics (rank_lo, rank_lo+1) per column -- what np.percentile's
+ * linear interpolation and np.median of an even count need -- in 4 radix passes of 16 bits plus one
+ * min pass; `same` != 0 returns the rank_lo value twice (rank_lo is the last element).
+ * out[2c], out[2c+1].  workspace: tb_select_pair_workspace_bytes(ncols). */
+size_t tb_select_pair_workspace_bytes(int32_t ncols);
+int tb_select_pair(const double* base, const int64_t* rows, int64_t stride, int64_t n, int32_t ncols,
+                   const int32_t* mult, int64_t rank_lo, int32_t same, void* workspace, double* out,
+                   tb_stream_t stream);
+
 /* multiplicity of each trimmed row among the 4n training draws: counts[idx[k]] += 1 */
 int tb_count_indices(const int64_t* idx, int64_t m, int32_t* counts, int64_t n, tb_stream_t stream);
 /* count-weighted mean and scatter of u[rows[j]] (multiplicity mult[j]):

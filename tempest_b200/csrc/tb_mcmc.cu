@@ -564,8 +564,9 @@ mcmc_begin_kernel(int64_t n, tb_mcmc_params p, const int32_t* __restrict__ assig
       }
       qcur[k] = q;
     }
-    atomicAdd(ctrl + C_BASE + K + c, 1.0);   // exact: integer counts < 2^53
+    if (assign) atomicAdd(ctrl + C_BASE + K + c, 1.0);   // exact: integer counts < 2^53
   }
+  if (!assign && blockIdx.x == 0 && threadIdx.x == 0) ctrl[C_BASE + K] = (double)n;   // single mode: every walker
 }
 
 __global__ void mcmc_update_kernel(tb_mcmc_params p, double* __restrict__ ctrl) {

@@ -275,6 +275,104 @@ __global__ void sel_finish_kernel(const SelState* __restrict__ st, double* __res
   if (i < count) out[i] = __longlong_as_double((long long)st[i].prefix);
 }
 
+// ---- adjacent order-statistic PAIR (ranks r, r+1): 4 MSD radix levels of 16 bits ------------------
+// np.percentile's two neighbours and np.median's middle pair are always adjacent ranks, so one
+// histogram per level resolves rank r exactly; rank r+1 is either the same value (multiplicity) or
+// the smallest key above it (one extra min pass).
+constexpr int kPairBins = 65536;
+constexpr int kPairLevels = 4;
+struct PairState {
+  unsigned long long prefix;   // resolved high bits of the rank-r key
+  long long rank;              // remaining rank inside the prefix class
+  unsigned long long next;     // min key strictly above (pass 5)
+  int need_next;               // 1: rank r+1 is not covered by the multiplicity of the rank-r value
+  int pad;
+};
+
+__global__ void pair_init_kernel(PairState* st, long long rank, int ncols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncols) { st[i].prefix = 0ull; st[i].rank = rank; st[i].next = ~0ull; st[i].need_next = 0; }
+}
+
+__global__ void __launch_bounds__(kBlock)
+pair_hist_kernel(const double* __restrict__ base, const int64_t* __restrict__ rows, int64_t stride_elems, int64_t n,
+                 int ncols, const int* __restrict__ mult, const PairState* __restrict__ st, int level,
+                 unsigned int* __restrict__ hist /* [ncols][65536] */) {
+  const int shift = 48 - 16 * level;
+  const int64_t total = n * ncols;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x; e0 < total; e0 += stride) {
+    const int64_t e = e0 + threadIdx.x;
+    int slot = -1;
+    unsigned int m = 0;
+    if (e < total) {
+      const int64_t j = e / ncols;
+      const int c = (int)(e - j * ncols);
+      m = mult ? (unsigned int)__ldg(mult + j) : 1u;
+      if (m) {
+        const int64_t r = rows ? __ldg(rows + j) : j;
+        const unsigned long long key = (unsigned long long)__double_as_longlong(__ldg(base + r * stride_elems + c));
+        const bool match = (level == 0) || ((key >> (shift + 16)) == (st[c].prefix >> (shift + 16)));
+        if (match) slot = (c << 16) | (int)((key >> shift) & 0xffffu);
+      }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, slot);
+    if (slot >= 0) {
+      const unsigned int sum = __reduce_add_sync(peers, m);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[slot], sum);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+pair_pick_kernel(PairState* st, const unsigned int* __restrict__ hist, int level) {
+  __shared__ unsigned long long part[1024];
+  const unsigned int* h = hist + (size_t)blockIdx.x * kPairBins;
+  const int per = kPairBins / 1024;
+  unsigned long long acc = 0;
+  for (int i = 0; i < per; ++i) acc += h[threadIdx.x * per + i];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    PairState s = st[blockIdx.x];
+    unsigned long long run = 0;
+    int t = 0;
+    for (; t < 1024; ++t) { if (run + part[t] > (unsigned long long)s.rank) break; run += part[t]; }
+    if (t == 1024) { t = 1023; run -= part[1023]; }
+    int b = t * per;
+    for (; b < t * per + per - 1; ++b) { if (run + h[b] > (unsigned long long)s.rank) break; run += h[b]; }
+    s.prefix |= ((unsigned long long)b) << (48 - 16 * level);
+    s.rank -= (long long)run;
+    if (level == kPairLevels - 1) s.need_next = ((unsigned long long)s.rank + 1ull < (unsigned long long)h[b]) ? 0 : 1;
+    st[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+pair_next_kernel(const double* __restrict__ base, const int64_t* __restrict__ rows, int64_t stride_elems, int64_t n,
+                 int ncols, const int* __restrict__ mult, PairState* __restrict__ st) {
+  const int64_t total = n * ncols;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t j = e / ncols;
+    const int c = (int)(e - j * ncols);
+    if (!st[c].need_next) continue;
+    if (mult && __ldg(mult + j) == 0) continue;
+    const int64_t r = rows ? __ldg(rows + j) : j;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(__ldg(base + r * stride_elems + c));
+    if (key > st[c].prefix && key < st[c].next) atomicMin(&st[c].next, key);
+  }
+}
+
+__global__ void pair_finish_kernel(const PairState* __restrict__ st, double* __restrict__ out, int ncols, int same) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncols) {
+    const double v1 = __longlong_as_double((long long)st[c].prefix);
+    out[2 * c] = v1;
+    out[2 * c + 1] = (same || !st[c].need_next) ? v1 : __longlong_as_double((long long)st[c].next);
+  }
+}
+
 // ---- multiplicities ---------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
 count_indices_kernel(const int64_t* __restrict__ idx, int64_t m, int* __restrict__ counts) {
@@ -706,6 +804,30 @@ int tb_select_ranks(const double* base, const int64_t* rows, int64_t stride, int
     sel_pick_kernel<<<slots, 256, 0, st>>>(state, hist, level);
   }
   sel_finish_kernel<<<(slots + 255) / 256, 256, 0, st>>>(state, out, slots);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+size_t tb_select_pair_workspace_bytes(int32_t ncols) {
+  return 256 + (sizeof(PairState) * (size_t)ncols + 255) / 256 * 256 + sizeof(unsigned int) * (size_t)ncols * kPairBins;
+}
+
+int tb_select_pair(const double* base, const int64_t* rows, int64_t stride, int64_t n, int32_t ncols,
+                   const int32_t* mult, int64_t rank_lo, int32_t same, void* workspace, double* out,
+                   tb_stream_t stream) {
+  if (n <= 0 || ncols <= 0 || ncols > 4096 || rank_lo < 0 || !base || !workspace || !out) return TB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  PairState* state = (PairState*)workspace;
+  unsigned int* hist = (unsigned int*)((char*)workspace + (sizeof(PairState) * (size_t)ncols + 255) / 256 * 256);
+  pair_init_kernel<<<(ncols + 255) / 256, 256, 0, st>>>(state, rank_lo, ncols);
+  const int grid = stream_grid(n * ncols, kBlock * 4, 8);
+  for (int level = 0; level < kPairLevels; ++level) {
+    cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (size_t)ncols * kPairBins, st);
+    pair_hist_kernel<<<grid, kBlock, 0, st>>>(base, rows, stride, n, ncols, mult, state, level, hist);
+    pair_pick_kernel<<<ncols, 1024, 0, st>>>(state, hist, level);
+  }
+  if (!same) pair_next_kernel<<<grid, kBlock, 0, st>>>(base, rows, stride, n, ncols, mult, state);
+  pair_finish_kernel<<<(ncols + 255) / 256, 256, 0, st>>>(state, out, ncols, same);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

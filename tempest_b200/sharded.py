@@ -80,6 +80,10 @@ class ShardedKernels(Kernels):
         _lib.check(lib.tb_select_stage(*args, 3, 0, st), "tb_select_stage")
         return out
 
+    def g_select_pair(self, base, rows, stride, m, ncols, mult, rank_lo, same, out):
+        ranks = torch.tensor([rank_lo, rank_lo if same else rank_lo + 1], dtype=torch.int64, device=self.device)
+        return self.g_select(base, rows, stride, m, ncols, mult, ranks, 2, out)
+
     # -- volume variation: partial moments + all-reduce ------------------------------------------------
     def volume_variation(self, u, w, n: int, d: int) -> float:
         lib, st = self.lib, stream_ptr()

@@ -256,6 +256,14 @@ class Kernels:
                                             ptr(sws), ptr(out), stream_ptr()), "tb_select_ranks")
         return out
 
+    def g_select_pair(self, base, rows, stride: int, m: int, ncols: int, mult, rank_lo: int, same: bool,
+                      out: torch.Tensor) -> torch.Tensor:
+        """Order statistics (rank_lo, rank_lo + 1) of every column -> out[2c], out[2c+1]."""
+        sws = self.ws.bytes("select_pair", self.lib.tb_select_pair_workspace_bytes(ncols))
+        _lib.check(self.lib.tb_select_pair(ptr(base), ptr(rows), stride, m, ncols, ptr(mult), int(rank_lo), int(same),
+                                           ptr(sws), ptr(out), stream_ptr()), "tb_select_pair")
+        return out
+
     # -- trim_weights (tools.py:10-55) ------------------------------------------------------
     def trim(self, w: torch.Tensor, n: int, ess: float = TRIM_ESS, bins: int = TRIM_BINS):
         """Normalises ``w`` IN PLACE (tools.py:36) and returns (idx int64[n_trim], w_trim[n_trim]).
@@ -315,10 +323,8 @@ class Kernels:
                     comp = (wc, m, n_glob - self.g_int(m))
             vals, m, below = comp
             lo, hi, g = pos[i]
-            ranks = self.ws.i64("trim_ranks", 2)
-            ranks.copy_(torch.tensor([lo - below, hi - below], dtype=torch.int64))
             sel = self.ws.f64("trim_sel", 2)
-            self.g_select(vals, None, 1, m, 1, None, ranks, 2, sel)
+            self.g_select_pair(vals, None, 1, m, 1, None, lo - below, hi == lo, sel)
             a, b = sel.cpu().numpy()
             thr = numpy_lerp(float(a), float(b), g)
             c, a1, a2 = self.g_sum3(vals, m, thr)
@@ -494,6 +500,7 @@ class Reweighter:
                 if need_probe:
                     ess, _ = self._probe(beta)
             stats = k.probe_out                     # (m, S1, ..., logZ) of the last probe == probe(beta)
+        core._stage("reweight:cv")
         w = k.weights(ens, beta, stats, core.weights_buffer())
         cv = k.volume_variation(ens.u, w, ens.n_total, ens.n_dim)     # reweight.py:417-419
         logz = float(stats[4].item())
@@ -540,7 +547,9 @@ class Trainer:
         k = core.k
         lib = k.lib
         st = stream_ptr()
+        core._stage("train:trim")
         idx, wt = k.trim(weights, ens.n_total)
+        core._stage("train:draws")
         core.trace["trim_idx"], core.trace["trim_w"] = idx, wt
         n_trim = int(idx.numel())                       # local; equals the global count on one GPU
         n_trim_glob = int(k.last_trim["n_trim"])
@@ -563,12 +572,13 @@ class Trainer:
         _lib.check(lib.tb_count_indices(ptr(didx), m_total, ptr(counts), max(n_trim, 1), st), "tb_count_indices")
         core.trace["train_draw_idx"] = didx
         # student.py:62: per-dimension median of the 4n-row multiset (even count: mean of the middle pair)
-        ranks = torch.tensor([m_total // 2 - 1, m_total // 2], dtype=torch.int64, device=core.device)
+        core._stage("train:median")
         pair = k.ws.f64("train_pair", 2 * d)
-        k.g_select(ens.u, idx, d, n_trim, d, counts, ranks, 2, pair)
+        k.g_select_pair(ens.u, idx, d, n_trim, d, counts, m_total // 2 - 1, False, pair)
         mean = torch.empty((1, d), dtype=F64, device=core.device)
         _lib.check(lib.tb_median_pairs(ptr(pair), d, ptr(mean), st), "tb_median_pairs")
         # student.py:63: Sigma = cov(ddof=1)*(M-1)/M + diag(var)/M from count-weighted moments
+        core._stage("train:moments")
         mws = k.ws.bytes("mom", lib.tb_moments_workspace_bytes(d))
         cmean = k.ws.f64("train_cmean", d)
         scatter = k.ws.f64("train_scatter", d * d)

@@ -355,3 +355,25 @@ def test_philox_uniforms_are_reproducible_and_uniform(env):
     # sharding invariance: offset selects a window of the same stream
     env._lib.check(env.lib.tb_philox_uniform(123, 5, 4, 1000, 100, env.ptr(b), env.sp()))
     assert torch.equal(a[1000:1100], b[:100])
+
+
+@pytest.mark.parametrize("n,d", [(1, 1), (2, 3), (4097, 1), (3001, 5), (200000, 10)])
+def test_select_pair_exact(env, n, d):
+    rng = np.random.default_rng(n + d)
+    u = rng.random((n, d))
+    if n > 10:
+        u[::7] = u[3]                                # heavy ties
+        u[5] = 1e-300
+    rows = rng.permutation(n)[: max(1, (2 * n) // 3)].astype(np.int64)
+    mult = rng.integers(0, 5, size=rows.size).astype(np.int32)
+    mult[0] = max(mult[0], 2)
+    expanded = np.repeat(u[rows], mult, axis=0)
+    srt = np.sort(expanded, axis=0)
+    m_total = expanded.shape[0]
+    du, dr, dm = dev_arr(env, u), dev_arr(env, rows), dev_arr(env, mult)
+    out = torch.empty(2 * d, dtype=torch.float64, device=env.dev)
+    for rank_lo in sorted({0, m_total // 2 - 1, m_total - 2, m_total - 1} & set(range(m_total))):
+        same = rank_lo == m_total - 1
+        env.k.g_select_pair(du, dr, d, rows.size, d, dm, rank_lo, same, out)
+        want = np.stack([srt[rank_lo], srt[rank_lo if same else rank_lo + 1]], axis=1)
+        np.testing.assert_array_equal(out.cpu().numpy().reshape(d, 2), want, err_msg=f"rank {rank_lo}")

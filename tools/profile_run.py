@@ -35,6 +35,12 @@ while core._not_termination():
     rows.append(row)
     print(json.dumps(row), flush=True)
 total = time.perf_counter() - t_all
+agg = {}
+for r in rows[5:]:
+    for k_, v in r.items():
+        if isinstance(v, float) and k_ not in ("beta", "wall_ms"):
+            agg[k_] = agg.get(k_, 0.0) + v
+print("stage sums (iterations 6..T, ms):", {k_: round(v, 1) for k_, v in sorted(agg.items(), key=lambda kv: -kv[1])})
 print(f"T={len(rows)} total {total:.3f} s  -> {len(rows) / total:.2f} it/s, calls {core.state.raw('calls')}, "
       f"{core.state.raw('calls') / total:.3e} evals/s")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
