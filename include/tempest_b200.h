@@ -172,6 +172,14 @@ int tb_select_pair(const double* base, const int64_t* rows, int64_t stride, int6
                    const int32_t* mult, int64_t rank_lo, int32_t same, void* workspace, double* out,
                    tb_stream_t stream);
 
+/* same pair for columns whose values lie in [0,1] (unit-cube coordinates): fixed-point bucket
+ * histogram -> compaction of the bucket(s) holding the two ranks -> exact in-block select.
+ * *overflow = 1 when a bucket held more than 65536 candidates (caller falls back to tb_select_pair). */
+size_t tb_unit_median_workspace_bytes(int32_t d);
+int tb_unit_median_pair(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
+                        int64_t rank_lo, void* workspace, double* out, int32_t* overflow,
+                        tb_stream_t stream);
+
 /* multiplicity of each trimmed row among the 4n training draws: counts[idx[k]] += 1 */
 int tb_count_indices(const int64_t* idx, int64_t m, int32_t* counts, int64_t n, tb_stream_t stream);
 /* count-weighted mean and scatter of u[rows[j]] (multiplicity mult[j]):

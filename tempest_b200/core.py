@@ -100,8 +100,9 @@ class SamplerCore:
 
     def weights_buffer(self) -> torch.Tensor:
         n = self.ensemble.n_total
+        self.k.ws.hint = self.ensemble.cap
         if self._weights is None or self._weights.numel() < n:
-            self._weights = torch.empty(max(int(n * 2), 1024), dtype=F64, device=self.device)
+            self._weights = torch.empty(max(int(n * 2), self.ensemble.cap, 1024), dtype=F64, device=self.device)
         return self._weights[:n]
 
     def mcmc_params(self, beta: float, mode_stats: Optional[ModeStats]) -> _lib.TbMcmcParams:

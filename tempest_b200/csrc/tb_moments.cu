@@ -373,6 +373,133 @@ __global__ void pair_finish_kernel(const PairState* __restrict__ st, double* __r
   }
 }
 
+// ---- middle pair of unit-interval columns (np.median of the 4n-row multiset, student.py:62) -------
+// Values live in [0,1] (unit-cube coordinates), so a 16-bit fixed-point bucket is a monotone key that
+// spreads evenly: one histogram pass, a pick, a compaction of the one or two buckets holding ranks
+// r and r+1, and an exact in-block radix select over the few thousand candidates.
+constexpr int kMedBuckets = 65536;
+constexpr int kMedCap = 1 << 16;     // candidates kept per column
+struct MedSel { int b1, b2; long long rank_local; unsigned int count; int overflow; };
+
+__device__ __forceinline__ int med_bucket(double v) {
+  int b = (int)(v * 65536.0);
+  return b < 0 ? 0 : (b > 65535 ? 65535 : b);
+}
+
+__global__ void __launch_bounds__(kBlock)
+med_hist_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, const int* __restrict__ mult, int64_t n,
+                int d, unsigned int* __restrict__ hist) {
+  const int64_t total = n * d;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t j = e / d;
+    const int c = (int)(e - j * d);
+    const unsigned int m = mult ? (unsigned int)__ldg(mult + j) : 1u;
+    if (!m) continue;
+    const int64_t r = rows ? __ldg(rows + j) : j;
+    atomicAdd(&hist[(size_t)c * kMedBuckets + med_bucket(__ldg(u + r * d + c))], m);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+med_pick_kernel(const unsigned int* __restrict__ hist, long long rank_lo, MedSel* __restrict__ sel) {
+  __shared__ unsigned long long part[1024];
+  const unsigned int* h = hist + (size_t)blockIdx.x * kMedBuckets;
+  const int per = kMedBuckets / 1024;
+  unsigned long long acc = 0;
+  for (int i = 0; i < per; ++i) acc += h[threadIdx.x * per + i];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    int t = 0;
+    for (; t < 1024; ++t) { if (run + part[t] > (unsigned long long)rank_lo) break; run += part[t]; }
+    if (t == 1024) { t = 1023; run -= part[1023]; }
+    int b = t * per;
+    for (; b < t * per + per - 1; ++b) { if (run + h[b] > (unsigned long long)rank_lo) break; run += h[b]; }
+    MedSel s;
+    s.b1 = b; s.rank_local = rank_lo - (long long)run; s.count = 0u; s.overflow = 0;
+    s.b2 = b;
+    if ((unsigned long long)s.rank_local + 1ull >= (unsigned long long)h[b]) {   // rank r+1 is in a later bucket
+      int nb = b + 1;
+      while (nb < kMedBuckets && h[nb] == 0u) ++nb;
+      s.b2 = nb < kMedBuckets ? nb : b;
+    }
+    sel[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+med_compact_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, const int* __restrict__ mult,
+                   int64_t n, int d, MedSel* __restrict__ sel, double* __restrict__ cval, unsigned int* __restrict__ cmul) {
+  const int64_t total = n * d;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int64_t j = e / d;
+    const int c = (int)(e - j * d);
+    const unsigned int m = mult ? (unsigned int)__ldg(mult + j) : 1u;
+    if (!m) continue;
+    const int64_t r = rows ? __ldg(rows + j) : j;
+    const double v = __ldg(u + r * d + c);
+    const int b = med_bucket(v);
+    if (b == sel[c].b1 || b == sel[c].b2) {
+      const unsigned int pos = atomicAdd(&sel[c].count, 1u);
+      if (pos < (unsigned int)kMedCap) { cval[(size_t)c * kMedCap + pos] = v; cmul[(size_t)c * kMedCap + pos] = m; }
+      else sel[c].overflow = 1;
+    }
+  }
+}
+
+// exact (rank_local, rank_local + 1) over one column's candidates: 8 MSD radix levels of 8 bits in smem
+__global__ void __launch_bounds__(1024)
+med_small_kernel(const MedSel* __restrict__ sel, const double* __restrict__ cval, const unsigned int* __restrict__ cmul,
+                 double* __restrict__ out, int* __restrict__ overflow) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long prefix, nextkey;
+  __shared__ long long rank;
+  __shared__ int need_next;
+  const MedSel s = sel[blockIdx.x];
+  if (s.overflow) { if (threadIdx.x == 0) *overflow = 1; return; }
+  const double* v = cval + (size_t)blockIdx.x * kMedCap;
+  const unsigned int* mu = cmul + (size_t)blockIdx.x * kMedCap;
+  const int cnt = (int)s.count;
+  if (threadIdx.x == 0) { prefix = 0ull; rank = s.rank_local; nextkey = ~0ull; need_next = 0; }
+  __syncthreads();
+  for (int level = 0; level < 8; ++level) {
+    const int shift = 56 - 8 * level;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned long long pre = prefix;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(v[i]);
+      if (level == 0 || (key >> (shift + 8)) == (pre >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 0xffu], mu[i]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long run = 0;
+      int b = 0;
+      for (; b < 255; ++b) { if (run + hist[b] > (unsigned long long)rank) break; run += hist[b]; }
+      prefix |= ((unsigned long long)b) << shift;
+      rank -= (long long)run;
+      if (level == 7) need_next = ((unsigned long long)rank + 1ull < (unsigned long long)hist[b]) ? 0 : 1;
+    }
+    __syncthreads();
+  }
+  if (need_next) {
+    const unsigned long long v1 = prefix;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(v[i]);
+      if (key > v1) atomicMin(&nextkey, key);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double a = __longlong_as_double((long long)prefix);
+    out[2 * blockIdx.x] = a;
+    out[2 * blockIdx.x + 1] = (need_next && nextkey != ~0ull) ? __longlong_as_double((long long)nextkey) : a;
+  }
+}
+
 // ---- multiplicities ---------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
 count_indices_kernel(const int64_t* __restrict__ idx, int64_t m, int* __restrict__ counts) {
@@ -804,6 +931,31 @@ int tb_select_ranks(const double* base, const int64_t* rows, int64_t stride, int
     sel_pick_kernel<<<slots, 256, 0, st>>>(state, hist, level);
   }
   sel_finish_kernel<<<(slots + 255) / 256, 256, 0, st>>>(state, out, slots);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+size_t tb_unit_median_workspace_bytes(int32_t d) {
+  return 512 + sizeof(unsigned int) * (size_t)d * kMedBuckets + sizeof(MedSel) * (size_t)d +
+         (sizeof(double) + sizeof(unsigned int)) * (size_t)d * kMedCap + 256 * 4;
+}
+
+int tb_unit_median_pair(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
+                        int64_t rank_lo, void* workspace, double* out, int32_t* overflow, tb_stream_t stream) {
+  if (n <= 0 || d <= 0 || d > 4096 || rank_lo < 0 || !u || !workspace || !out || !overflow) return TB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  char* p = (char*)workspace;
+  unsigned int* hist = (unsigned int*)p;             p += (sizeof(unsigned int) * (size_t)d * kMedBuckets + 255) / 256 * 256;
+  MedSel* sel = (MedSel*)p;                          p += (sizeof(MedSel) * (size_t)d + 255) / 256 * 256;
+  double* cval = (double*)p;                         p += sizeof(double) * (size_t)d * kMedCap;
+  unsigned int* cmul = (unsigned int*)p;
+  cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (size_t)d * kMedBuckets, st);
+  cudaMemsetAsync(overflow, 0, sizeof(int32_t), st);
+  const int grid = stream_grid(n * d, kBlock * 4, 8);
+  med_hist_kernel<<<grid, kBlock, 0, st>>>(u, rows, mult, n, d, hist);
+  med_pick_kernel<<<d, 1024, 0, st>>>(hist, rank_lo, sel);
+  med_compact_kernel<<<grid, kBlock, 0, st>>>(u, rows, mult, n, d, sel, cval, cmul);
+  med_small_kernel<<<d, 1024, 0, st>>>(sel, cval, cmul, out, overflow);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

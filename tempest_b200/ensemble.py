@@ -63,10 +63,15 @@ class PersistentEnsemble:
             self._reserve(capacity)
 
     # -- capacity -----------------------------------------------------------------------
+    RESERVE_GENERATIONS = 48      # a C4-like run stores ~36 generations; growth beyond this doubles
+
     def _reserve(self, need: int) -> None:
         if need <= self.cap:
             return
-        new_cap = max(need, int(self.cap * 2), 1024)
+        # first allocation: room for RESERVE_GENERATIONS generations of this size, so that neither the
+        # store nor the per-N_total scratch buffers are re-allocated (cudaMalloc/cudaFree stalls) mid-run
+        first = need * self.RESERVE_GENERATIONS if self.cap == 0 else 0
+        new_cap = max(need, int(self.cap * 2), first, 1024)
         for name, shape in (("u", (new_cap, self.n_dim)), ("logl", (new_cap,)), ("C", (new_cap,))):
             old = getattr(self, name)
             new = torch.empty(shape, dtype=torch.float64, device=self.device)

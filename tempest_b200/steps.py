@@ -32,32 +32,38 @@ class Workspace:
         self.device = device
         self.lib = _lib.load()
         self._buf = {}
+        self.hint = 0          # capacity of the persistent ensemble: N_total-sized scratch is allocated once
+
+    def _size(self, n: int) -> int:
+        if self.hint and n > self.hint // 64:
+            return max(int(n), self.hint) if n <= self.hint else int(n * 2)
+        return max(int(n * 2), 16)
 
     def bytes(self, name: str, nbytes: int) -> torch.Tensor:
         t = self._buf.get(name)
         if t is None or t.numel() < nbytes:
-            t = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            t = torch.zeros(max(int(nbytes) * 2, 256), dtype=torch.uint8, device=self.device)
             self._buf[name] = t
         return t
 
     def f64(self, name: str, n: int) -> torch.Tensor:
         t = self._buf.get(name)
         if t is None or t.numel() < n:
-            t = torch.empty(max(int(n * 2), 16), dtype=F64, device=self.device)
+            t = torch.empty(self._size(n), dtype=F64, device=self.device)
             self._buf[name] = t
         return t[:n]
 
     def i64(self, name: str, n: int) -> torch.Tensor:
         t = self._buf.get(name)
         if t is None or t.numel() < n:
-            t = torch.empty(max(int(n * 2), 16), dtype=torch.int64, device=self.device)
+            t = torch.empty(self._size(n), dtype=torch.int64, device=self.device)
             self._buf[name] = t
         return t[:n]
 
     def i32(self, name: str, n: int) -> torch.Tensor:
         t = self._buf.get(name)
         if t is None or t.numel() < n:
-            t = torch.empty(max(int(n * 2), 16), dtype=torch.int32, device=self.device)
+            t = torch.empty(self._size(n), dtype=torch.int32, device=self.device)
             self._buf[name] = t
         return t[:n]
 
@@ -574,7 +580,15 @@ class Trainer:
         # student.py:62: per-dimension median of the 4n-row multiset (even count: mean of the middle pair)
         core._stage("train:median")
         pair = k.ws.f64("train_pair", 2 * d)
-        k.g_select_pair(ens.u, idx, d, n_trim, d, counts, m_total // 2 - 1, False, pair)
+        done = False
+        if not k.sharded:
+            mws_ = k.ws.bytes("unit_median", lib.tb_unit_median_workspace_bytes(d))
+            ovf = k.ws.i32("median_ovf", 1)
+            _lib.check(lib.tb_unit_median_pair(ptr(ens.u), ptr(idx), ptr(counts), n_trim, d, m_total // 2 - 1,
+                                               ptr(mws_), ptr(pair), ptr(ovf), st), "tb_unit_median_pair")
+            done = int(ovf.item()) == 0
+        if not done:
+            k.g_select_pair(ens.u, idx, d, n_trim, d, counts, m_total // 2 - 1, False, pair)
         mean = torch.empty((1, d), dtype=F64, device=core.device)
         _lib.check(lib.tb_median_pairs(ptr(pair), d, ptr(mean), st), "tb_median_pairs")
         # student.py:63: Sigma = cov(ddof=1)*(M-1)/M + diag(var)/M from count-weighted moments

@@ -377,3 +377,32 @@ def test_select_pair_exact(env, n, d):
         env.k.g_select_pair(du, dr, d, rows.size, d, dm, rank_lo, same, out)
         want = np.stack([srt[rank_lo], srt[rank_lo if same else rank_lo + 1]], axis=1)
         np.testing.assert_array_equal(out.cpu().numpy().reshape(d, 2), want, err_msg=f"rank {rank_lo}")
+
+
+@pytest.mark.parametrize("n,d,width", [(3, 1, 1.0), (5000, 10, 1.0), (200000, 10, 0.01), (50000, 4, 1e-6), (4000, 2, 0.0)])
+def test_unit_median_pair_exact(env, n, d, width):
+    """np.median's middle pair of the count-expanded rows (student.py:62), incl. concentrated and
+    fully degenerate columns (every value in one bucket)."""
+    rng = np.random.default_rng(n * 7 + d)
+    u = 0.4 + width * rng.random((n, d)) * 0.5
+    u[0] = 0.0
+    u[-1] = 1.0
+    rows = rng.permutation(n)[: max(2, (3 * n) // 4)].astype(np.int64)
+    mult = rng.integers(0, 6, size=rows.size).astype(np.int32)
+    mult[:2] = 1
+    if mult.sum() % 2:
+        mult[0] += 1
+    m_total = int(mult.sum())
+    srt = np.sort(np.repeat(u[rows], mult, axis=0), axis=0)
+    du, dr, dm = dev_arr(env, u), dev_arr(env, rows), dev_arr(env, mult)
+    out = torch.empty(2 * d, dtype=torch.float64, device=env.dev)
+    ovf = torch.zeros(1, dtype=torch.int32, device=env.dev)
+    ws = torch.zeros(env.lib.tb_unit_median_workspace_bytes(d), dtype=torch.uint8, device=env.dev)
+    r = m_total // 2 - 1
+    env._lib.check(env.lib.tb_unit_median_pair(env.ptr(du), env.ptr(dr), env.ptr(dm), rows.size, d, r, env.ptr(ws),
+                                               env.ptr(out), env.ptr(ovf), env.sp()))
+    if int(ovf.item()):
+        assert rows.size * 1.0 > 65536          # only legitimate when a bucket really is that crowded
+        env.k.g_select_pair(du, dr, d, rows.size, d, dm, r, False, out)
+    np.testing.assert_array_equal(out.cpu().numpy().reshape(d, 2), np.stack([srt[r], srt[r + 1]], axis=1))
+    assert np.array_equal(np.median(np.repeat(u[rows], mult, axis=0), axis=0), out.cpu().numpy().reshape(d, 2).mean(1))
