@@ -142,7 +142,7 @@ __device__ __forceinline__ void bm_pair32(uint32_t a, uint32_t b, double& z0, do
   z1 = (double)(r * s);
 }
 
-template <int D>
+template <int D, bool TPCN, bool TAPE>
 __global__ void __launch_bounds__(kMcmcBlock)
 mcmc_step_fast(StepArgs a) {
   if (a.ctrl[C_DONE] != 0.0) return;
@@ -154,18 +154,25 @@ mcmc_step_fast(StepArgs a) {
   __shared__ int s_used[B];
   __shared__ int s_mode[B];
   const int K = a.p.n_modes;
-  const bool tpcn = a.p.sampler == TB_SAMPLE_TPCN;
-  const bool tape = a.p.rng_mode == TB_RNG_TAPE;
+  constexpr bool tpcn = TPCN;
+  constexpr bool tape = TAPE;
   const int step = (int)a.ctrl[C_STEPS];
   double* s_mean = sm;
   double* s_chol = s_mean + K * D;
-  double* s_inv = s_chol + K * D * D;
+  double* s_inv = s_chol + K * D * D;                // symmetric form: diagonal as is, off-diagonals doubled (upper)
   double* s_dof = s_inv + K * D * D;
   double* s_sig = s_dof + K;
   double* s_part = s_sig + K;                        // [4][K] per-warp alpha sums
+  double* s_prior = s_part + 4 * K;                  // [2*D] lo, scale
   for (int e = threadIdx.x; e < K * D; e += B) s_mean[e] = __ldg(a.p.mode_mean + e);
-  for (int e = threadIdx.x; e < K * D * D; e += B) { s_chol[e] = __ldg(a.p.mode_chol + e); s_inv[e] = __ldg(a.p.mode_inv + e); }
+  for (int e = threadIdx.x; e < K * D * D; e += B) {
+    s_chol[e] = __ldg(a.p.mode_chol + e);
+    const int i = (e % (D * D)) / D, j = e % D;
+    const double v = __ldg(a.p.mode_inv + e);
+    s_inv[e] = (j > i) ? 2.0 * v : v;               // q = sum_i d_i * sum_{j>=i} S_ij d_j
+  }
   for (int e = threadIdx.x; e < K; e += B) { s_dof[e] = __ldg(a.p.mode_dof + e); s_sig[e] = a.ctrl[C_BASE + e]; }
+  for (int e = threadIdx.x; e < 2 * D; e += B) s_prior[e] = __ldg(a.p.prior_params + e);
   __syncthreads();
 
   const int t = threadIdx.x, lane = t & 31, wbase = t & ~31;
@@ -177,6 +184,8 @@ mcmc_step_fast(StepArgs a) {
   int err = tape_over ? 1 : 0;
   int c = 0;
   double logl = 0.0, q = 0.0;
+  uint32_t acc_word = 0u;
+  bool have_acc_word = false;
   // ---- phase A -------------------------------------------------------------------------------
   if (valid) {
     c = a.assign ? a.assign[k] : 0;
@@ -193,11 +202,11 @@ mcmc_step_fast(StepArgs a) {
         for (int i = 0; i < D; ++i) dq[i] = urow[i] - mu[i];
         q = 0.0;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
+        for (int i = 0; i < D; ++i) {
           double y = 0.0;
 #pragma unroll
-          for (int i = 0; i < D; ++i) y += dq[i] * IV[i * D + j];
-          q += y * dq[j];
+          for (int j = i; j < D; ++j) y += IV[i * D + j] * dq[j];
+          q += dq[i] * y;
         }
         a.qcur[k] = q;
       } else q = a.qcur[k];
@@ -217,7 +226,10 @@ mcmc_step_fast(StepArgs a) {
           const double v = v1 * v1 * v1;
           const double uu = ((double)r.z + 0.5) * 2.3283064365386963e-10;
           const double x2 = n0 * n0;
-          if (uu < 1.0 - 0.0331 * x2 * x2 || log(uu) < 0.5 * x2 + dd * (1.0 - v + log(v))) { g = dd * v; break; }
+          if (uu < 1.0 - 0.0331 * x2 * x2 || log(uu) < 0.5 * x2 + dd * (1.0 - v + log(v))) {
+            g = dd * v; acc_word = r.w; have_acc_word = true;     // the 4th word of this block feeds the accept test
+            break;
+          }
         }
       }
       const double gscale = 2.0 / (dof + q);
@@ -274,11 +286,15 @@ mcmc_step_fast(StepArgs a) {
       }
       double prop[D];
       bool inside = have;
+      if (!TAPE) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] *= cmul;        // (c L) z == L (c z) up to rounding; tape mode keeps the reference order
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         double lz = 0.0;
 #pragma unroll
-        for (int j = 0; j <= i; ++j) lz += (cmul * L[i * D + j]) * z[j];
+        for (int j = 0; j <= i; ++j) lz += TAPE ? (cmul * L[i * D + j]) * z[j] : L[i * D + j] * z[j];
         double v = s_x[i][wl] + lz;
         const int kind = a.p.bc_kind ? a.p.bc_kind[i] : 0;
         v = bc_apply(v, kind);
@@ -320,7 +336,7 @@ mcmc_step_fast(StepArgs a) {
     const double dof = s_dof[c];
     double prop[D], x[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) { prop[i] = s_x[i][t]; x[i] = prior_affine(a.p.prior_params, D, i, prop[i]); }
+    for (int i = 0; i < D; ++i) { prop[i] = s_x[i][t]; x[i] = __dadd_rn(s_prior[i], __dmul_rn(s_prior[D + i], prop[i])); }
     const double logl_new = eval_like(a.p.like_id, a.p.like_params, D, x);
     double factor = 0.0, q_new = 0.0;
     if (tpcn) {
@@ -328,11 +344,11 @@ mcmc_step_fast(StepArgs a) {
 #pragma unroll
       for (int i = 0; i < D; ++i) dn[i] = prop[i] - mu[i];
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
+      for (int i = 0; i < D; ++i) {
         double y = 0.0;
 #pragma unroll
-        for (int i = 0; i < D; ++i) y += dn[i] * IV[i * D + j];
-        q_new += y * dn[j];
+        for (int j = i; j < D; ++j) y += IV[i * D + j] * dn[j];
+        q_new += dn[i] * y;
       }
       const double hd = -0.5 * ((double)D + dof);
       const double A = hd * log(1.0 + q_new / dof);
@@ -345,6 +361,7 @@ mcmc_step_fast(StepArgs a) {
     alpha = al;
     double ur;
     if (tape) ur = a.tape.acc_u[(int64_t)step * a.n + k];
+    else if (have_acc_word) ur = ((double)acc_word + 0.5) * 2.3283064365386963e-10;   // 32-bit uniform in (0,1)
     else {
       const uint4 r = rng.block((uint32_t)(slot0 + t), (uint32_t)((slot0 + t) >> 32), (uint32_t)step, RNG_ACCEPT << 24);
       ur = u53(r.x, r.y);
@@ -634,18 +651,26 @@ int launch_steps(const StepArgs& a, int count, cudaStream_t st) {
   return e == cudaSuccess ? TB_OK : (int)e;
 }
 
-template <int D>
-int launch_fast(const StepArgs& a, int count, cudaStream_t st) {
+template <int D, bool TPCN, bool TAPE>
+int launch_fast_variant(const StepArgs& a, int count, cudaStream_t st) {
   const int K = a.p.n_modes;
-  const size_t smem = sizeof(double) * ((size_t)K * D + 2 * (size_t)K * D * D + 2 * K + 4 * K);
+  const size_t smem = sizeof(double) * ((size_t)K * D + 2 * (size_t)K * D * D + 2 * K + 4 * K + 2 * D);
   if (smem > 40 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(mcmc_step_fast<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mcmc_step_fast<D, TPCN, TAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
   const int grid = (int)((a.n + kMcmcBlock - 1) / kMcmcBlock);
-  for (int s = 0; s < count; ++s) mcmc_step_fast<D><<<grid, kMcmcBlock, smem, st>>>(a);
+  for (int s = 0; s < count; ++s) mcmc_step_fast<D, TPCN, TAPE><<<grid, kMcmcBlock, smem, st>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? TB_OK : (int)e;
+}
+
+template <int D>
+int launch_fast(const StepArgs& a, int count, cudaStream_t st) {
+  const bool tpcn = a.p.sampler == TB_SAMPLE_TPCN, tape = a.p.rng_mode == TB_RNG_TAPE;
+  if (tpcn) return tape ? launch_fast_variant<D, true, true>(a, count, st) : launch_fast_variant<D, true, false>(a, count, st);
+  return tape ? launch_fast_variant<D, false, true>(a, count, st) : launch_fast_variant<D, false, false>(a, count, st);
 }
 
 inline bool has_fast_path(int d) {
