@@ -192,6 +192,16 @@ int tb_counted_moments(const double* u, const int64_t* rows, const int32_t* mult
 /* ------------------------------------------------------------------------------------
  * (d) mutation.   ref: steps/mutate.py:76-200, mcmc.py:104-323
  * ---------------------------------------------------------------------------------- */
+/* In-kernel exchange across the GPUs of one node (sharded runs): peer[r] is rank r's exchange buffer
+ * (tb_xgpu_buffer_bytes() bytes of zero-initialised symmetric / peer-mapped memory) as addressed from
+ * this device; seq is the next unused exchange sequence number (>= 1, consecutive across calls). */
+typedef struct tb_xgpu {
+  int32_t rank, world;
+  uint64_t seq;
+  double* peer[8];
+} tb_xgpu;
+size_t tb_xgpu_buffer_bytes(void);
+
 typedef struct tb_tape {
   /* TB_RNG_TAPE: variates recorded from the oracle's stream */
   const double* gamma;    /* [steps][n]  standard-gamma variates (tpCN) */
@@ -218,6 +228,8 @@ typedef struct tb_mcmc_params {
   const double* mode_inv;           /* [K][d][d] */
   const double* mode_dof;           /* [K] */
   const uint8_t* bc_kind;           /* [d] 0 strict, 1 periodic, 2 reflective; NULL = all strict */
+  const tb_xgpu* xgpu;              /* HOST pointer or NULL: fuse the per-step all-reduce into the step kernel
+                                     * (exchange number of step s of this call is xgpu->seq + s) */
 } tb_mcmc_params;
 
 /* warm-up draw at beta = 0: u = uniforms (tape `prior_u` [n][d] or Philox), x = prior(u),
@@ -266,6 +278,11 @@ size_t tb_select_hist_offset(int32_t ncols, int32_t nranks);
 int tb_moments_partial(const double* u, const int64_t* rows, const double* w, const int32_t* mult, int64_t n,
                        int32_t d, double inv_norm, int32_t do_mean, int32_t do_cov, void* workspace,
                        double* mean, double* cov, tb_stream_t stream);
+/* tb_next_beta with the per-probe merge of the ranks' (m,S1,S2) triples fused into the kernel over
+ * peer memory: every rank launches it with the same arguments; consumes result16[6] exchanges */
+int tb_next_beta_x(const double* logl, const double* C, int64_t n_total, double beta_prev,
+                   double ess_target, int32_t flags, void* workspace, double* result16,
+                   double* probe_log, int32_t probe_log_cap, const tb_xgpu* xgpu, tb_stream_t stream);
 /* apply sigma adaptation + stop rule from all-reduced per-step totals (defer_update = 1) */
 int tb_mcmc_update(const tb_mcmc_params* p, double* ctrl, tb_stream_t stream);
 

@@ -22,6 +22,10 @@ class TbTape(C.Structure):
                 ("steps", c_i32)]
 
 
+class TbXgpu(C.Structure):
+    _fields_ = [("rank", c_i32), ("world", c_i32), ("seq", c_u64), ("peer", PTR * 8)]
+
+
 class TbMcmcParams(C.Structure):
     _fields_ = [
         ("n_dim", c_i32), ("n_modes", c_i32), ("sampler", c_i32), ("rng_mode", c_i32),
@@ -30,6 +34,7 @@ class TbMcmcParams(C.Structure):
         ("beta", c_f64), ("seed", c_u64), ("iteration", c_u64), ("slot_offset", c_i64),
         ("n_global", c_i64), ("like_params", PTR), ("prior_params", PTR), ("mode_mean", PTR),
         ("mode_chol", PTR), ("mode_inv", PTR), ("mode_dof", PTR), ("bc_kind", PTR),
+        ("xgpu", C.POINTER(TbXgpu)),
     ]
 
 
@@ -87,6 +92,8 @@ SIGNATURES = {
     "tb_select_hist_offset": (SIZE, [c_i32, c_i32]),
     "tb_moments_partial": (c_i32, [PTR, PTR, PTR, PTR, c_i64, c_i32, c_f64, c_i32, c_i32, PTR, PTR, PTR, PTR]),
     "tb_mcmc_update": (c_i32, [C.POINTER(TbMcmcParams), PTR, PTR]),
+    "tb_xgpu_buffer_bytes": (SIZE, []),
+    "tb_next_beta_x": (c_i32, [PTR, PTR, c_i64, c_f64, c_f64, c_i32, PTR, PTR, PTR, c_i32, C.POINTER(TbXgpu), PTR]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -122,7 +129,7 @@ KERNELS_PER_CALL = {
     "tb_binade_hist": 1, "tb_masked_sums": 1, "tb_compact_ge": 3, "tb_select_ranks": 14, "tb_count_indices": 1,
     "tb_counted_moments": 2, "tb_prior_draw": 1, "tb_transform": 1, "tb_mcmc_begin": 2,
     "tb_mcmc_steps": lambda args: int(args[9]), "tb_philox_uniform": 1, "tb_search_right_sharded": 1,
-    "tb_scale_inplace": 1, "tb_select_stage": 1, "tb_select_pair": 11, "tb_unit_median_pair": 4, "tb_moments_partial": 2, "tb_mcmc_update": 1,
+    "tb_scale_inplace": 1, "tb_select_stage": 1, "tb_select_pair": 11, "tb_unit_median_pair": 4, "tb_next_beta_x": 1, "tb_moments_partial": 2, "tb_mcmc_update": 1,
 }
 launch_count = 0
 

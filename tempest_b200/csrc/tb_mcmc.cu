@@ -12,6 +12,7 @@
 // HBM traffic per step: the active set (u row, logl, q) is read once and written on accept;
 // proposals, normals and likelihood terms never leave registers.
 #include "tb_like.cuh"
+#include "tb_xgpu.cuh"
 
 static int tb_force_generic_mcmc = 0;
 
@@ -41,6 +42,7 @@ struct StepArgs {
   double* qcur;
   McmcWs* ws;
   double* ctrl;
+  tb_xgpu x;          // world > 1: the per-step totals are exchanged over peer memory inside the kernel
 };
 
 __device__ __forceinline__ double bc_apply(double v, int kind) {
@@ -70,6 +72,22 @@ __device__ void finish_step(const StepArgs& a, int K, int nparts) {
     tot[c] = t;
   }
   __syncthreads();
+  if (a.x.world > 1) {
+    // fused collective: exchange this rank's (sum alpha per mode, accepted, proposals, error) with every
+    // peer over NVLink and fold them in rank order, then adapt sigma / evaluate the stop rule right here
+    if (threadIdx.x == 0) {
+      double all[kXMaxRanks * 15];
+      const unsigned long long seq = a.x.seq + (unsigned long long)a.ctrl[C_STEPS];
+      xgpu_allgather(a.x, seq, tot, W, all);
+      for (int c = 0; c < W; ++c) {
+        double t = 0.0;
+        for (int r = 0; r < a.x.world; ++r) t += all[r * W + c];
+        tot[c] = t;
+      }
+      apply_step_update(a.p, a.ctrl, tot, K);
+    }
+    return;
+  }
   if (a.p.defer_update) {
     // sharded run: leave this rank's totals for the host to all-reduce; tb_mcmc_update applies them
     for (int c = threadIdx.x; c < W; c += blockDim.x) a.ctrl[C_BASE + 3 * K + c] = tot[c];
@@ -752,6 +770,12 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
   if (tape) a.tape = *tape; else { a.tape.gamma = nullptr; a.tape.acc_u = nullptr; a.tape.z = nullptr;
                                     a.tape.z_off = nullptr; a.tape.z_cnt = nullptr; a.tape.steps = 0; }
   a.assign = assign; a.u = u; a.logl = logl; a.qcur = qcur; a.ws = (McmcWs*)workspace; a.ctrl = ctrl;
+  if (p->xgpu) {
+    a.x = *p->xgpu;
+    if (a.x.world < 1 || a.x.world > kXMaxRanks || a.x.seq < 1 || p->n_modes + 3 > 15) return TB_ERR_ARG;
+    a.p.defer_update = 0;
+  } else { a.x.rank = 0; a.x.world = 1; a.x.seq = 1; for (int i = 0; i < 8; ++i) a.x.peer[i] = nullptr; }
+  a.p.xgpu = nullptr;
   cudaStream_t st = as_stream(stream);
   const int d = p->n_dim;
   if (!tb_force_generic_mcmc) {

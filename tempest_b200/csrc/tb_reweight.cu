@@ -7,6 +7,7 @@
 // Probe = 16 B / particle streamed once (HBM-bound); the N_total x T log-sum-exp of the
 // reference is folded into the cached column C (fp64-pipe bound, done once per generation).
 #include "tb_common.cuh"
+#include "tb_xgpu.cuh"
 
 namespace {
 using namespace tb;
@@ -40,6 +41,7 @@ struct ProbeWs {            // workspace layout (device)
   unsigned int barrier;     // grid barrier counter (next_beta)
   unsigned int pad[2];
   double partial[2][kMaxPartials][4];  // double-buffered {m, S1, S2, n_nonfinite}
+  double xmerged[2][4];                // sharded runs: cross-GPU merge of the ranks' triples (published by CTA 0)
 };
 
 // exp(d) for d in (-40, 0]: Cody-Waite reduction by ln2, degree-13 Taylor polynomial on |r| <= ln2/2
@@ -195,7 +197,7 @@ constexpr double kTiny = 2.2250738585072014e-308;
 __global__ void __launch_bounds__(kBlock, 5)
 next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n,
                  double beta_prev, double target, int flags, ProbeWs* ws, double* __restrict__ result,
-                 double* __restrict__ plog, int plog_cap) {
+                 double* __restrict__ plog, int plog_cap, tb_xgpu xg) {
   __shared__ double smem[160];
   __shared__ double sh_beta;
   __shared__ int sh_done;
@@ -217,6 +219,25 @@ next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, 
     }
     grid_barrier(&ws->barrier);
     merge_partials(ws->partial[buf], gridDim.x, smem, e, bad);
+    if (xg.world > 1) {
+      // fused collective: CTA 0 exchanges this rank's triple with every peer over NVLink, folds the
+      // ranks' triples in rank order and publishes the result to the other CTAs of this GPU
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double mine[4] = {e.m, e.s1, e.s2, bad};
+        double all[kXMaxRanks * 4];
+        xgpu_allgather(xg, xg.seq + (unsigned long long)nprobe, mine, 4, all);
+        Ess3 g; g.init();
+        double gb = 0.0;
+        for (int r = 0; r < xg.world; ++r) { g.merge(all[4 * r], all[4 * r + 1], all[4 * r + 2]); gb += all[4 * r + 3]; }
+        ws->xmerged[buf][0] = g.m; ws->xmerged[buf][1] = g.s1; ws->xmerged[buf][2] = g.s2; ws->xmerged[buf][3] = gb;
+        __threadfence();
+      }
+      grid_barrier(&ws->barrier);
+      if (threadIdx.x == 0) {
+        e.m = __ldcg(&ws->xmerged[buf][0]); e.s1 = __ldcg(&ws->xmerged[buf][1]);
+        e.s2 = __ldcg(&ws->xmerged[buf][2]); bad = __ldcg(&ws->xmerged[buf][3]);
+      }
+    }
     if (threadIdx.x == 0) {
       double ess = (e.s1 * e.s1) / e.s2;
       if (blockIdx.x == 0 && plog != nullptr && nprobe < plog_cap) { plog[2 * nprobe] = beta; plog[2 * nprobe + 1] = ess; }
@@ -325,7 +346,19 @@ int tb_log_weights(const double* logl, const double* C, int64_t n, double beta, 
 int tb_next_beta(const double* logl, const double* C, int64_t n, double beta_prev, double ess_target,
                  int32_t flags, void* workspace, double* result, double* probe_log, int32_t probe_log_cap,
                  tb_stream_t stream) {
+  return tb_next_beta_x(logl, C, n, beta_prev, ess_target, flags, workspace, result, probe_log, probe_log_cap,
+                        nullptr, stream);
+}
+
+size_t tb_xgpu_buffer_bytes(void) { return sizeof(double) * 2 * kXMaxRanks * kXSlotDoubles; }
+
+int tb_next_beta_x(const double* logl, const double* C, int64_t n, double beta_prev, double ess_target,
+                   int32_t flags, void* workspace, double* result, double* probe_log, int32_t probe_log_cap,
+                   const tb_xgpu* xgpu, tb_stream_t stream) {
   if (n <= 0 || !logl || !C || !workspace || !result) return TB_ERR_ARG;
+  tb_xgpu xg;
+  if (xgpu) { xg = *xgpu; if (xg.world < 1 || xg.world > kXMaxRanks || xg.seq < 1) return TB_ERR_ARG; }
+  else { xg.rank = 0; xg.world = 1; xg.seq = 1; for (int i = 0; i < 8; ++i) xg.peer[i] = nullptr; }
   static int max_coresident = 0;
   if (max_coresident == 0) {
     int per_sm = 0;
@@ -343,7 +376,7 @@ int tb_next_beta(const double* logl, const double* C, int64_t n, double beta_pre
   cudaError_t e = cudaMemsetAsync(&ws->barrier, 0, sizeof(unsigned int), as_stream(stream));
   if (e != cudaSuccess) return (int)e;
   void* args[] = {(void*)&logl, (void*)&C, (void*)&n, (void*)&beta_prev, (void*)&ess_target, (void*)&flags,
-                  (void*)&ws, (void*)&result, (void*)&probe_log, (void*)&probe_log_cap};
+                  (void*)&ws, (void*)&result, (void*)&probe_log, (void*)&probe_log_cap, (void*)&xg};
   e = cudaLaunchCooperativeKernel((void*)next_beta_kernel, dim3(grid), dim3(kBlock), args, 0, as_stream(stream));
   if (e != cudaSuccess) return (int)e;
   return TB_OK;

@@ -25,6 +25,49 @@ class ShardedKernels(Kernels):
         super().__init__(device)
         self.comm = comm
         self.sharded = True
+        self.xgpu = self._setup_xgpu()
+
+    # -- peer-mapped exchange buffers for the in-kernel collectives (tb_xgpu.cuh) --------------------
+    def _setup_xgpu(self):
+        """Symmetric memory rendezvous: every rank learns the device address of every peer's exchange
+        buffer.  Returns None (NCCL collectives between launches are used instead) when the platform
+        cannot map peer memory."""
+        if self.comm.world > 8:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            n = int(self.lib.tb_xgpu_buffer_bytes()) // 8
+            buf = symm.empty(n, dtype=F64, device=self.device)
+            buf.zero_()
+            handle = symm.rendezvous(buf, torch.distributed.group.WORLD if self.comm.group is None else self.comm.group)
+            torch.cuda.synchronize()
+            self.comm.allreduce_sum_(torch.zeros(1, device=self.device))      # everyone has zeroed its buffer
+            x = _lib.TbXgpu()
+            x.rank, x.world, x.seq = self.comm.rank, self.comm.world, 1
+            for r in range(self.comm.world):
+                x.peer[r] = int(handle.buffer_ptrs[r])
+            self._xbuf, self._xhandle = buf, handle
+            return x
+        except Exception as exc:      # pragma: no cover - platform dependent
+            import warnings
+
+            warnings.warn(f"peer-mapped exchange buffers unavailable ({type(exc).__name__}: {exc}); "
+                          "falling back to NCCL collectives between launches")
+            return None
+
+    def consume_exchanges(self, count: int) -> None:
+        self.xgpu.seq += int(count)
+
+    def next_beta(self, ens, beta_prev: float, target: float, flags: int, log_cap: int = 512):
+        """Whole ESS bracket + bisection in one cooperative launch per rank; the per-probe merge of the
+        ranks' (m, S1, S2) runs inside the kernel over NVLink peer memory."""
+        res = self.ws.f64("nb_res", 16)
+        plog = self.ws.f64("nb_log", 2 * log_cap)
+        _lib.check(self.lib.tb_next_beta_x(ptr(ens.logl), ptr(ens.C), ens.n_total, float(beta_prev), float(target),
+                                           int(flags), ptr(self._probe_ws), ptr(res), ptr(plog), log_cap,
+                                           C.byref(self.xgpu), stream_ptr()), "tb_next_beta_x")
+        return res, plog
 
     # -- reweighting: merge the per-shard (m, S1, S2) triples in rank order -------------------------
     def probe(self, ens: PersistentEnsemble, beta: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:

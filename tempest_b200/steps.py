@@ -483,7 +483,7 @@ class Reweighter:
         target = self.ess_ratio * n
         dynamic = self.volume_variation is not None
         k = core.k
-        if not dynamic and self.device_search and not k.sharded:
+        if not dynamic and self.device_search and (not k.sharded or k.xgpu is not None):
             beta, ess, stats = self._device_search(beta_prev, target)
         else:
             lo, hi = self._ess_bracket(beta_prev, target)
@@ -533,6 +533,8 @@ class Reweighter:
         nprobe = int(h[6])
         hp = plog[: 2 * min(nprobe, 512)].cpu().numpy().reshape(-1, 2)
         self.probe_log.extend((float(b), float(e)) for b, e in hp)
+        if k.sharded:
+            k.consume_exchanges(nprobe)              # one peer-memory exchange per probe
         if h[8] != 0.0:
             raise FloatingPointError(f"{int(h[8])} non-finite log-weights in the persistent ensemble")
         return float(h[0]), float(h[4]), res[1:7]     # (m, S1, S2, ESS, logZ, .) like tb_probe's out
@@ -708,13 +710,18 @@ class Mutator:
         n_cap = cfg.n_max_steps * d
         launched = 0
         budget = min(n_min, n_cap)
+        fused = k.sharded and k.xgpu is not None and K + 3 <= 15
         if k.sharded:
+            k.comm.allreduce_sum_(ctrl[8 + K: 8 + 2 * K])          # walkers per mode: global counts
+        if fused:
+            params.xgpu = C.pointer(k.xgpu)                        # per-step all-reduce fused into the step kernel
+            params.defer_update = 0
+        elif k.sharded:
             from .sharded import sharded_mcmc_loop
 
-            k.comm.allreduce_sum_(ctrl[8 + K: 8 + 2 * K])          # walkers per mode: global counts
             h, launched = sharded_mcmc_loop(core, params, tape_ref, u, logl, qcur, ws, ctrl, min(n_min, n_cap),
                                             n_cap, self.CHUNK)
-        while not k.sharded:
+        while fused or not k.sharded:
             if tape is not None:
                 budget = min(budget, tape.steps - launched)
             if budget > 0:
@@ -729,6 +736,8 @@ class Mutator:
                     f"tape holds {tape.steps} MCMC steps but the device stop rule has not fired after {launched}")
             budget = min(self.CHUNK, n_cap - launched)
         core.n_mcmc_launches += launched
+        if fused:
+            k.consume_exchanges(int(h[0]))                         # one exchange per executed step
         if h[4] != 0.0:
             raise RuntimeError(f"MCMC kernel error flag {h[4]} (1: tape exhausted, 2: proposal never entered the cube)")
         steps = int(h[0])
