@@ -180,6 +180,14 @@ int tb_unit_median_pair(const double* u, const int64_t* rows, const int32_t* mul
                         int64_t rank_lo, void* workspace, double* out, int32_t* overflow,
                         tb_stream_t stream);
 
+/* same bucket -> compact -> exact-select scheme for ONE column of non-negative doubles known to lie in
+ * [lo_value, hi_value] (weights above a binade edge): buckets are affine in the bit pattern.  The
+ * histogram is kept in the workspace, so follow-up calls on the same data pass build_hist = 0.
+ * workspace: tb_unit_median_workspace_bytes(1). */
+int tb_bucket_select_pair(const double* v, int64_t n, int64_t rank_lo, int32_t same, double lo_value,
+                          double hi_value, int32_t build_hist, void* workspace, double* out2,
+                          int32_t* overflow, tb_stream_t stream);
+
 /* multiplicity of each trimmed row among the 4n training draws: counts[idx[k]] += 1 */
 int tb_count_indices(const int64_t* idx, int64_t m, int32_t* counts, int64_t n, tb_stream_t stream);
 /* count-weighted mean and scatter of u[rows[j]] (multiplicity mult[j]):

@@ -6,6 +6,7 @@
 // HBM layout: u[N_total][d] row-major fp64, w[N_total] fp64.  All reductions publish one
 // partial per CTA and the last CTA to finish merges them in a fixed order (deterministic).
 #include "tb_common.cuh"
+#include <string.h>
 
 namespace {
 using namespace tb;
@@ -381,14 +382,23 @@ constexpr int kMedBuckets = 65536;
 constexpr int kMedCap = 1 << 16;     // candidates kept per column
 struct MedSel { int b1, b2; long long rank_local; unsigned int count; int overflow; };
 
-__device__ __forceinline__ int med_bucket(double v) {
-  int b = (int)(v * 65536.0);
-  return b < 0 ? 0 : (b > 65535 ? 65535 : b);
+// monotone 16-bit bucket of a non-negative double: shift < 0 -> unit-interval fixed point
+// floor(v * 65536); otherwise (bits(v) - key_lo) >> shift (piecewise-linear in log space, for weights)
+struct BucketMap { unsigned long long key_lo; int shift; };
+__device__ __forceinline__ int med_bucket(double v, BucketMap bm) {
+  if (bm.shift < 0) {
+    int b = (int)(v * 65536.0);
+    return b < 0 ? 0 : (b > 65535 ? 65535 : b);
+  }
+  const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+  if (key <= bm.key_lo) return 0;
+  const unsigned long long b = (key - bm.key_lo) >> bm.shift;
+  return b > 65535ull ? 65535 : (int)b;
 }
 
 __global__ void __launch_bounds__(kBlock)
 med_hist_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, const int* __restrict__ mult, int64_t n,
-                int d, unsigned int* __restrict__ hist) {
+                int d, unsigned int* __restrict__ hist, BucketMap bm) {
   const int64_t total = n * d;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -397,7 +407,7 @@ med_hist_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, 
     const unsigned int m = mult ? (unsigned int)__ldg(mult + j) : 1u;
     if (!m) continue;
     const int64_t r = rows ? __ldg(rows + j) : j;
-    atomicAdd(&hist[(size_t)c * kMedBuckets + med_bucket(__ldg(u + r * d + c))], m);
+    atomicAdd(&hist[(size_t)c * kMedBuckets + med_bucket(__ldg(u + r * d + c), bm)], m);
   }
 }
 
@@ -431,7 +441,8 @@ med_pick_kernel(const unsigned int* __restrict__ hist, long long rank_lo, MedSel
 
 __global__ void __launch_bounds__(kBlock)
 med_compact_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, const int* __restrict__ mult,
-                   int64_t n, int d, MedSel* __restrict__ sel, double* __restrict__ cval, unsigned int* __restrict__ cmul) {
+                   int64_t n, int d, MedSel* __restrict__ sel, double* __restrict__ cval, unsigned int* __restrict__ cmul,
+                   BucketMap bm) {
   const int64_t total = n * d;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -441,7 +452,7 @@ med_compact_kernel(const double* __restrict__ u, const int64_t* __restrict__ row
     if (!m) continue;
     const int64_t r = rows ? __ldg(rows + j) : j;
     const double v = __ldg(u + r * d + c);
-    const int b = med_bucket(v);
+    const int b = med_bucket(v, bm);
     if (b == sel[c].b1 || b == sel[c].b2) {
       const unsigned int pos = atomicAdd(&sel[c].count, 1u);
       if (pos < (unsigned int)kMedCap) { cval[(size_t)c * kMedCap + pos] = v; cmul[(size_t)c * kMedCap + pos] = m; }
@@ -453,7 +464,7 @@ med_compact_kernel(const double* __restrict__ u, const int64_t* __restrict__ row
 // exact (rank_local, rank_local + 1) over one column's candidates: 8 MSD radix levels of 8 bits in smem
 __global__ void __launch_bounds__(1024)
 med_small_kernel(const MedSel* __restrict__ sel, const double* __restrict__ cval, const unsigned int* __restrict__ cmul,
-                 double* __restrict__ out, int* __restrict__ overflow) {
+                 double* __restrict__ out, int* __restrict__ overflow, int same) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long prefix, nextkey;
   __shared__ long long rank;
@@ -496,7 +507,7 @@ med_small_kernel(const MedSel* __restrict__ sel, const double* __restrict__ cval
   if (threadIdx.x == 0) {
     const double a = __longlong_as_double((long long)prefix);
     out[2 * blockIdx.x] = a;
-    out[2 * blockIdx.x + 1] = (need_next && nextkey != ~0ull) ? __longlong_as_double((long long)nextkey) : a;
+    out[2 * blockIdx.x + 1] = (need_next && nextkey != ~0ull && !same) ? __longlong_as_double((long long)nextkey) : a;
   }
 }
 
@@ -940,24 +951,45 @@ size_t tb_unit_median_workspace_bytes(int32_t d) {
          (sizeof(double) + sizeof(unsigned int)) * (size_t)d * kMedCap + 256 * 4;
 }
 
-int tb_unit_median_pair(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
-                        int64_t rank_lo, void* workspace, double* out, int32_t* overflow, tb_stream_t stream) {
-  if (n <= 0 || d <= 0 || d > 4096 || rank_lo < 0 || !u || !workspace || !out || !overflow) return TB_ERR_ARG;
-  cudaStream_t st = as_stream(stream);
+static int bucket_pair_launch(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
+                              int64_t rank_lo, int same, BucketMap bm, int build_hist, void* workspace, double* out,
+                              int32_t* overflow, cudaStream_t st) {
   char* p = (char*)workspace;
   unsigned int* hist = (unsigned int*)p;             p += (sizeof(unsigned int) * (size_t)d * kMedBuckets + 255) / 256 * 256;
   MedSel* sel = (MedSel*)p;                          p += (sizeof(MedSel) * (size_t)d + 255) / 256 * 256;
   double* cval = (double*)p;                         p += sizeof(double) * (size_t)d * kMedCap;
   unsigned int* cmul = (unsigned int*)p;
-  cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (size_t)d * kMedBuckets, st);
   cudaMemsetAsync(overflow, 0, sizeof(int32_t), st);
   const int grid = stream_grid(n * d, kBlock * 4, 8);
-  med_hist_kernel<<<grid, kBlock, 0, st>>>(u, rows, mult, n, d, hist);
+  if (build_hist) {
+    cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (size_t)d * kMedBuckets, st);
+    med_hist_kernel<<<grid, kBlock, 0, st>>>(u, rows, mult, n, d, hist, bm);
+  }
   med_pick_kernel<<<d, 1024, 0, st>>>(hist, rank_lo, sel);
-  med_compact_kernel<<<grid, kBlock, 0, st>>>(u, rows, mult, n, d, sel, cval, cmul);
-  med_small_kernel<<<d, 1024, 0, st>>>(sel, cval, cmul, out, overflow);
-  TB_CHECK_LAUNCH();
-  return TB_OK;
+  med_compact_kernel<<<grid, kBlock, 0, st>>>(u, rows, mult, n, d, sel, cval, cmul, bm);
+  med_small_kernel<<<d, 1024, 0, st>>>(sel, cval, cmul, out, overflow, same);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TB_OK : (int)e;
+}
+
+int tb_unit_median_pair(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
+                        int64_t rank_lo, void* workspace, double* out, int32_t* overflow, tb_stream_t stream) {
+  if (n <= 0 || d <= 0 || d > 4096 || rank_lo < 0 || !u || !workspace || !out || !overflow) return TB_ERR_ARG;
+  BucketMap bm; bm.key_lo = 0ull; bm.shift = -1;
+  return bucket_pair_launch(u, rows, mult, n, d, rank_lo, 0, bm, 1, workspace, out, overflow, as_stream(stream));
+}
+
+int tb_bucket_select_pair(const double* v, int64_t n, int64_t rank_lo, int32_t same, double lo_value, double hi_value,
+                          int32_t build_hist, void* workspace, double* out2, int32_t* overflow, tb_stream_t stream) {
+  if (n <= 0 || rank_lo < 0 || !v || !workspace || !out2 || !overflow || !(lo_value >= 0.0) || !(hi_value >= lo_value))
+    return TB_ERR_ARG;
+  unsigned long long klo, khi;
+  memcpy(&klo, &lo_value, 8);
+  memcpy(&khi, &hi_value, 8);
+  BucketMap bm; bm.key_lo = klo; bm.shift = 0;
+  while (((khi - klo) >> bm.shift) > 65535ull) ++bm.shift;
+  return bucket_pair_launch(v, nullptr, nullptr, n, 1, rank_lo, same, bm, build_hist, workspace, out2, overflow,
+                            as_stream(stream));
 }
 
 size_t tb_select_pair_workspace_bytes(int32_t ncols) {

@@ -308,9 +308,13 @@ class Kernels:
 
         cache = {}
         comp = None  # (values tensor, local count, global count below the compacted set)
+        hist_built = [False]
+        comp_lo = 0.0
+        nzb = np.nonzero(h_cnt)[0]
+        w_max = float(np.ldexp(1.0, int(nzb.max()) - 1022)) if nzb.size else 1.0     # upper edge of the top binade
 
         def exact(i: int):
-            nonlocal comp
+            nonlocal comp, comp_lo
             if i in cache:
                 return cache[i]
             if comp is None:
@@ -320,6 +324,7 @@ class Kernels:
                     comp = (w, n, 0)
                 else:
                     edge = float(np.ldexp(1.0, b0 - 1023))
+                    comp_lo = edge
                     wc = self.ws.f64("trim_comp", n)
                     nout = self.ws.i64("trim_nout", 1)
                     cws = self.ws.bytes("compact", lib.tb_compact_workspace_bytes(n))
@@ -330,7 +335,18 @@ class Kernels:
             vals, m, below = comp
             lo, hi, g = pos[i]
             sel = self.ws.f64("trim_sel", 2)
-            self.g_select_pair(vals, None, 1, m, 1, None, lo - below, hi == lo, sel)
+            done = False
+            if not self.sharded and m > 0:
+                # bucket histogram over the compacted tail is built once and reused by every evaluation
+                bws = self.ws.bytes("bucket_pair", lib.tb_unit_median_workspace_bytes(1))
+                ovf = self.ws.i32("bucket_ovf", 1)
+                _lib.check(lib.tb_bucket_select_pair(ptr(vals), m, lo - below, int(hi == lo), comp_lo, w_max,
+                                                     int(not hist_built[0]), ptr(bws), ptr(sel), ptr(ovf), st),
+                           "tb_bucket_select_pair")
+                hist_built[0] = True
+                done = int(ovf.item()) == 0
+            if not done:
+                self.g_select_pair(vals, None, 1, m, 1, None, lo - below, hi == lo, sel)
             a, b = sel.cpu().numpy()
             thr = numpy_lerp(float(a), float(b), g)
             c, a1, a2 = self.g_sum3(vals, m, thr)
