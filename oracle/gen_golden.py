@@ -50,7 +50,55 @@ def cases():
         "shell4_n48_dynamic": (
             UniformPrior(-6.0, 6.0, 4), TwinShells(4),
             dict(n_dim=4, n_particles=48, clustering=False, volume_variation=0.5), 192, 14),
+        # hierarchical-GMM clustering on (defaults): four separated modes in 2-D (config C2, small)
+        "mix2_n64_clustered": (
+            UniformPrior(-10.0, 10.0, 2), IsotropicMixture.four_corners(2),
+            dict(n_dim=2, n_particles=64, clustering=True), 256, 21),
+        # clustering with a cluster cap, no normalisation, refit every 2nd iteration, two shells
+        "shell3_n96_clustered_cap": (
+            UniformPrior(-6.0, 6.0, 3), TwinShells(3),
+            dict(n_dim=3, n_particles=96, clustering=True, normalize=False, cluster_every=2,
+                 n_max_clusters=3, split_threshold=0.5), 256, 22),
     }
+
+
+def cluster_cases():
+    """name -> (X[n,d], w[n], HierarchicalGaussianMixture kwargs): stand-alone fits (cluster.py)."""
+    rs = np.random.RandomState(77)
+
+    def blobs(n, d, k, spread, lo=0.2, hi=0.8):
+        c = rs.rand(k, d) * (hi - lo) + lo
+        lab = rs.randint(0, k, n)
+        return c[lab] + spread * rs.randn(n, d)
+
+    out = {}
+    out["cluster_blobs2d"] = (blobs(600, 2, 4, 0.02), rs.rand(600) ** 2, dict(normalize=True))
+    out["cluster_blobs5d"] = (blobs(500, 5, 3, 0.03), rs.rand(500) ** 3, dict(normalize=True))
+    out["cluster_single10d"] = (blobs(300, 10, 1, 0.05), rs.rand(300), dict(normalize=True))
+    out["cluster_raw3d_cap"] = (blobs(400, 3, 3, 0.01), rs.rand(400),
+                                dict(normalize=False, max_iterations=1, min_points=12, threshold_modifier=0.5))
+    x = blobs(256, 2, 2, 0.04)
+    x[:, 1] = 0.5 + 1e-3 * (x[:, 1] - 0.5)      # nearly degenerate second axis
+    out["cluster_thin2d"] = (x, np.ones(256), dict(normalize=True))
+    return out
+
+
+def run_reference_cluster(ref_root, x, w, kw):
+    sys.path.insert(0, ref_root)
+    from tempest.cluster import GaussianMixture, HierarchicalGaussianMixture  # the reference
+
+    h = HierarchicalGaussianMixture(**kw).fit(x, w)
+    rs = np.random.RandomState(3)
+    y = rs.rand(512, x.shape[1])
+    out = dict(x=x, w=w, y=y, labels=h.labels_, centres=np.array(h.cluster_centers_),
+               covs=np.array(h.cluster_covariances_), weights=h.cluster_weights_,
+               n_clusters=np.array(h.n_clusters_), predict_y=h.predict(y), predict_x=h.predict(x))
+    for k in (1, 2):
+        g = GaussianMixture(n_components=k, random_state=42).fit(x, w)
+        out.update({f"gmm{k}_weights": g.weights_, f"gmm{k}_means": g.means_, f"gmm{k}_covs": g.covariances_,
+                    f"gmm{k}_n_iter": np.array(g.n_iter_), f"gmm{k}_bic": np.array(g.bic(x)),
+                    f"gmm{k}_labels": g.predict(x), f"gmm{k}_lower": np.array(g.lower_bound_)})
+    return out
 
 
 def run_reference(ref_root, prior, like, kwargs, n_total, seed):
@@ -92,6 +140,18 @@ def main():
         np.savez_compressed(path, **out)
         print(f"{name}: T={len(out['h_beta'])} logz={float(out['final_logz']):.6f} "
               f"steps={out['h_steps'].sum():.0f} -> {path} ({os.path.getsize(path)/1024:.0f} KiB)")
+    main_cluster(a.ref, a.out, a.only)
+
+
+def main_cluster(ref, out_dir, only=None):
+    for name, (x, w, kw) in cluster_cases().items():
+        if only and only != name:
+            continue
+        out = run_reference_cluster(ref, x, w, kw)
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: K={int(out['n_clusters'])} gmm2 iters={int(out['gmm2_n_iter'])} -> {path} "
+              f"({os.path.getsize(path)/1024:.0f} KiB)")
 
 
 if __name__ == "__main__":

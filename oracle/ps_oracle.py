@@ -60,6 +60,9 @@ class LegacyStream:
     def __init__(self, seed: Optional[int] = None, rs: Optional[np.random.RandomState] = None):
         self.rs = rs if rs is not None else np.random.RandomState(seed)
 
+    def reseed(self, seed: int) -> None:  # np.random.seed(seed) on the global stream (cluster.py:94-95)
+        self.rs = np.random.RandomState(seed)
+
     def uniform_matrix(self, n: int, d: int) -> np.ndarray:  # np.random.rand(n, d)
         return self.rs.rand(n, d)
 
@@ -393,6 +396,34 @@ def mode_stats_global(u: np.ndarray, weights: np.ndarray, uniforms: np.ndarray,
     return ModeStats(mean.reshape(1, -1), cov.reshape(1, *cov.shape), np.array([dof])), idx
 
 
+def mode_stats_particles(u: np.ndarray, weights: np.ndarray, labels: np.ndarray, stream,
+                         factor: int = 4, record: Optional[dict] = None) -> ModeStats:
+    """One Student-t mode per *distinct predicted label* -- tempest/modes.py:131-219.  Members keep
+    their order (:191), weights are renormalised inside the cluster (:193-194), ``4 n_c`` rows are
+    drawn with replacement (:197-201) and fitted (:204-209).  Mode k is the k-th distinct label
+    (:188), so walkers carrying a label beyond K index out of range downstream."""
+    w = weights / np.sum(weights)
+    means, covs, dofs, unis, draws, members_all = [], [], [], [], [], []
+    for label in np.unique(labels):
+        members = np.where(labels == label)[0]
+        wc = w[members]
+        wc = wc / np.sum(wc)
+        uni = stream.uniform_vector(factor * len(members))
+        idx = legacy_choice_indices(wc, uni)
+        mean, cov, dof = student_fit(u[members][idx])
+        if not np.isfinite(dof):
+            dof = DOF_FALLBACK
+        means.append(mean)
+        covs.append(cov)
+        dofs.append(dof)
+        unis.append(uni)
+        draws.append(idx)
+        members_all.append(members)
+    if record is not None:
+        record.update(train_u=np.concatenate(unis), draw_idx=draws, members=members_all)
+    return ModeStats(np.array(means), np.array(covs), np.array(dofs))
+
+
 # --------------------------------------------------------------------------------------
 # Boundaries (mcmc.py:326-411)
 # --------------------------------------------------------------------------------------
@@ -543,10 +574,10 @@ def mcmc_mutate(
 
 
 # --------------------------------------------------------------------------------------
-# Full PS loop (core.py:110-185, 360-374; steps/*.py) -- clustering=False path
+# Full PS loop (core.py:110-185, 360-374; steps/*.py)
 # --------------------------------------------------------------------------------------
 class OraclePS:
-    """Persistent Sampling with ``clustering=False`` restated end to end.
+    """Persistent Sampling restated end to end (``clustering`` on or off).
 
     ``iterate()`` is ``SamplerCore.execute_iteration`` (core.py:162-185): reweight
     (steps/reweight.py:341-495) -> train (steps/train.py:65-127, global branch) -> resample
@@ -556,7 +587,8 @@ class OraclePS:
     def __init__(
         self, prior_transform, log_likelihood, n_dim, n_particles=None, ess_ratio=2.0,
         volume_variation=None, periodic=None, reflective=None, sample="tpcn", n_steps=None,
-        n_max_steps=None, resample="mult", stream=None, record=False,
+        n_max_steps=None, resample="mult", stream=None, record=False, clustering=False,
+        normalize=True, cluster_every=1, split_threshold=1.0, n_max_clusters=None,
     ):
         self.prior_transform = prior_transform
         self.log_likelihood = log_likelihood
@@ -573,6 +605,12 @@ class OraclePS:
         self.resample = resample
         self.stream = stream if stream is not None else LegacyStream(0)
         self.record = record
+        self.clustering = bool(clustering)
+        self.normalize = bool(normalize)
+        self.cluster_every = int(cluster_every)
+        self.split_threshold = float(split_threshold)
+        self.n_max_clusters = n_max_clusters
+        self.clusterer = None
         self.hist: Dict[str, list] = {k: [] for k in (
             "u", "x", "logl", "iter", "logz", "calls", "steps", "efficiency", "ess", "cv",
             "acceptance", "beta")}
@@ -635,6 +673,29 @@ class OraclePS:
             return ModeStats(np.zeros((1, d)), np.eye(d).reshape(1, d, d), np.array([DOF_FALLBACK]))
         idx, w_trim, i_bin = trim_weights(weights)
         u = np.concatenate(self.hist["u"])[idx]
+        if self.clustering:  # train.py:97-115
+            from .cluster_oracle import fit_hierarchy
+
+            it = self.cur["iter"]
+            if it % self.cluster_every == 0 or it == 0:
+                cap = self.n_max_clusters  # core.py:59-69
+                self.clusterer = fit_hierarchy(
+                    u, w_trim, self.stream, normalize=self.normalize,
+                    max_iterations=1000 if cap is None else cap - 1,
+                    min_points=None if cap is None else 4 * d,
+                    threshold_modifier=self.split_threshold)
+            labels = self.clusterer.predict(u)
+            rec: dict = {}
+            stats = mode_stats_particles(u, w_trim, labels, self.stream, record=rec)
+            tape["train_u"] = rec["train_u"]
+            trace.update(trim_idx=idx, trim_w=w_trim, trim_bin=i_bin, train_labels=labels,
+                         train_draw_idx=rec["draw_idx"], n_clusters=self.clusterer.n_clusters,
+                         cluster_centres=np.array(self.clusterer.centres),
+                         cluster_covs=np.array(self.clusterer.covs),
+                         cluster_weights=self.clusterer.weights.copy(),
+                         mode_mean=stats.means.copy(), mode_cov=stats.covs.copy(),
+                         mode_chol=stats.chol.copy(), mode_inv=stats.inv.copy(), mode_dof=stats.dofs.copy())
+            return stats
         uni = self.stream.uniform_vector(4 * len(idx))
         stats, draw_idx = mode_stats_global(u, w_trim, uni)
         tape["train_u"] = uni
@@ -661,7 +722,9 @@ class OraclePS:
             tape["resample_u"] = np.array([u0])
         trace["resample_idx"] = idx
         trace["resample_p"] = weights.copy()
-        self.cur.update(u=u[idx], x=x[idx], logl=logl[idx], assignments=np.zeros(n, dtype=int))
+        assign = self.clusterer.predict(u[idx]) if self.clustering else np.zeros(n, dtype=int)  # :92-94
+        trace["assignments"] = assign
+        self.cur.update(u=u[idx], x=x[idx], logl=logl[idx], assignments=assign)
 
     def _mutate(self, stats, tape, trace):
         n, d = self.n_particles, self.n_dim

@@ -12,16 +12,17 @@ import pytest
 
 from conftest import GOLDEN
 from oracle import ps_oracle as po
-from oracle.gen_golden import cases
+from oracle import cluster_oracle as co
+from oracle.gen_golden import cases, cluster_cases
 
 CASES = cases()
+CLUSTER_CASES = cluster_cases()
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_reproduces_reference_run(name):
     prior, like, kw, n_total, seed = CASES[name]
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    kw = {k: v for k, v in kw.items() if k != "clustering"}
     o = po.OraclePS(prior, like, stream=po.LegacyStream(seed), **kw)
     o.run(n_total)
     assert len(o.hist["beta"]) == len(g["h_beta"])
@@ -37,6 +38,47 @@ def test_oracle_reproduces_reference_run(name):
     np.testing.assert_array_equal(logw, g["post_logw"])
     _, w2, _ = o.posterior(trim_importance_weights=False)
     np.testing.assert_array_equal(w2, g["post_w_untrimmed"])
+
+
+@pytest.mark.parametrize("name", sorted(CLUSTER_CASES))
+def test_cluster_oracle_reproduces_reference_fit(name):
+    """cluster.py restated (oracle/cluster_oracle.py) against the reference's own fits: the EM
+    iteration counts, labels, centres, covariances, BICs and predictions must be identical."""
+    x, w, kw = CLUSTER_CASES[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    np.testing.assert_array_equal(x, g["x"])
+    np.testing.assert_array_equal(w, g["w"])
+    h = co.fit_hierarchy(x, w, po.LegacyStream(0), **kw)
+    assert h.n_clusters == int(g["n_clusters"])
+    np.testing.assert_array_equal(h.labels, g["labels"])
+    np.testing.assert_array_equal(np.array(h.centres), g["centres"])
+    np.testing.assert_array_equal(np.array(h.covs), g["covs"])
+    np.testing.assert_array_equal(h.weights, g["weights"])
+    np.testing.assert_array_equal(h.predict(g["y"]), g["predict_y"])
+    np.testing.assert_array_equal(h.predict(x), g["predict_x"])
+    for k in (1, 2):
+        m = co.fit_mixture(x, w, k, po.LegacyStream(0))
+        assert m.n_iter == int(g[f"gmm{k}_n_iter"])
+        np.testing.assert_array_equal(m.weights, g[f"gmm{k}_weights"])
+        np.testing.assert_array_equal(m.means, g[f"gmm{k}_means"])
+        np.testing.assert_array_equal(m.covs, g[f"gmm{k}_covs"])
+        assert m.bic(x) == float(g[f"gmm{k}_bic"])
+        assert m.lower_bound == float(g[f"gmm{k}_lower"])
+        np.testing.assert_array_equal(m.predict(x), g[f"gmm{k}_labels"])
+
+
+def test_mvn_logpdf_matches_scipy():
+    from scipy.stats import multivariate_normal
+
+    rs = np.random.RandomState(9)
+    for d in (1, 2, 5, 12):
+        a = rs.randn(d, d)
+        cov = a @ a.T / d + 1e-3 * np.eye(d)
+        mean = rs.randn(d)
+        x = rs.randn(64, d)
+        np.testing.assert_array_equal(co.mvn_logpdf(x, mean, cov), multivariate_normal.logpdf(x, mean=mean, cov=cov))
+    with pytest.raises(np.linalg.LinAlgError):
+        co.mvn_logpdf(np.zeros((2, 2)), np.zeros(2), np.array([[1.0, 1.0], [1.0, 1.0]]))
 
 
 def test_boundary_known_answers():
