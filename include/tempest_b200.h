@@ -294,6 +294,62 @@ int tb_next_beta_x(const double* logl, const double* C, int64_t n_total, double 
 /* apply sigma adaptation + stop rule from all-reduced per-step totals (defer_update = 1) */
 int tb_mcmc_update(const tb_mcmc_params* p, double* ctrl, tb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * (e') hierarchical Gaussian-mixture clustering.   ref: tempest/cluster.py
+ *
+ * One weighted mixture fit lives in a device PARAMETER BLOCK of tb_gmm_block_doubles(d,k) doubles:
+ * a 16-double header {lower bound, done, completed passes (= n_iter once done), last bound, -, -, -,
+ * bound-only result, ...} followed by weights[k], means[k,d], covariances[k,d,d], the inverse lower
+ * Cholesky factors of cov + reg I, log normalisers, ok flags and M-step scratch; tb_gmm_offsets
+ * returns {weights, means, covs, linv, lognorm, ok, mass, total} offsets in doubles.
+ * x is row-major [.,d]; rows (nullable) lists the member rows of the cluster being fitted, in the
+ * reference's order; sw are the members' normalised sample weights (position-indexed).
+ * ---------------------------------------------------------------------------------- */
+int64_t tb_gmm_block_doubles(int32_t d, int32_t k);
+int tb_gmm_offsets(int32_t d, int32_t k, int64_t* out8);
+size_t tb_gmm_workspace_bytes(void);
+/* weighted k-means++ (cluster.py:139-158): p_i = min_c |x_i - c|^2 sw_i over the first k centres;
+ * tb_kpp_pick: j = searchsorted(run, frac*run[n-1]) (left), centre <- x[rows[j]] */
+int tb_kpp_prob(const double* x, const int64_t* rows, const double* sw, int64_t n, int32_t d,
+                const double* centres, int32_t k, double* p, tb_stream_t stream);
+int tb_kpp_pick(const double* run, int64_t n, double frac, const double* x, const int64_t* rows,
+                int32_t d, double* centre, int64_t* picked, tb_stream_t stream);
+/* initial parameters from the centres (cluster.py:160-168): responsibilities exp(-|x-c_k|^2/2),
+ * normalised, then one M-step.  wr: k*n doubles of scratch (r*sw columns). */
+int tb_gmm_init(const double* x, const int64_t* rows, const double* sw, int64_t n, int32_t d, int32_t k,
+                const double* centres, double* block, double* wr, void* workspace,
+                void* mom_workspace, double reg, tb_stream_t stream);
+/* enqueue `passes` EM passes (cluster.py:103-121, 172-250, 264-283); passes after convergence
+ * (new bound - bound < tol) or after max_iter return immediately; block[1] != 0 when finished,
+ * block[2] = n_iter */
+int tb_gmm_em(const double* x, const int64_t* rows, const double* sw, int64_t n, int32_t d, int32_t k,
+              double* block, double* wr, void* workspace, void* mom_workspace, double reg, double tol,
+              int32_t max_iter, int32_t passes, tb_stream_t stream);
+/* block[7] = sum_i sw_i log(sum_k w_k N_k(x_i) + 1e-10); sw NULL = 1/n (the BIC term, cluster.py:329-338) */
+int tb_gmm_bound(const double* x, const int64_t* rows, const double* sw, int64_t n, int32_t d, int32_t k,
+                 double* block, void* workspace, tb_stream_t stream);
+/* factor cov + reg I of every component of a block whose weights/means/covs were written by the
+ * caller; a failed factorisation falls back to `fallback` * I (cluster.py:185-188, 667-670) */
+int tb_gmm_prepare(double* block, int32_t d, int32_t k, double reg, double fallback, tb_stream_t stream);
+/* labels_i = argmax_k log(w_k + 1e-10) + log N(x_i; mu_k, Sigma_k + reg I) (cluster.py:285-308,
+ * 633-696); lo/hi (nullable pair): min-max normalise x on the fly, (x - lo)/((hi - lo) + 1e-10) */
+int tb_gmm_predict(const double* x, const int64_t* rows, int64_t n, int32_t d, int32_t k,
+                   const double* block, const double* lo, const double* hi, int32_t skip_bad,
+                   int32_t* labels, tb_stream_t stream);
+/* column minima / maxima of x[rows] (cluster.py:437-438) and the normalised gather (:382) */
+size_t tb_col_minmax_workspace_bytes(int32_t d);
+int tb_col_minmax(const double* x, const int64_t* rows, int64_t n, int32_t d, void* workspace,
+                  double* lo, double* hi, tb_stream_t stream);
+int tb_gather_normalised(const double* x, const int64_t* rows, int64_t n, int32_t d, const double* lo,
+                         const double* hi, double* out, tb_stream_t stream);
+/* out_i = src[idx_i] */
+int tb_take(const double* src, const int64_t* idx, int64_t n, double* out, tb_stream_t stream);
+/* order-preserving split of a member list by a 0 / non-0 label (cluster.py:495-496):
+ * out_zero[0 : n - *n_one], out_one[0 : *n_one]; members NULL = positions */
+size_t tb_split_workspace_bytes(int64_t n);
+int tb_split_by_label(const int32_t* labels, const int64_t* members, int64_t n, void* workspace,
+                      int64_t* out_zero, int64_t* out_one, int64_t* n_one, tb_stream_t stream);
+
 /* testing hook: route every n_dim through the generic (runtime-d) step kernel instead of the
  * compile-time-d fast path (tape mode must give identical decisions on both) */
 int tb_set_mcmc_generic(int32_t on);

@@ -54,11 +54,11 @@ def cases():
         "mix2_n64_clustered": (
             UniformPrior(-10.0, 10.0, 2), IsotropicMixture.four_corners(2),
             dict(n_dim=2, n_particles=64, clustering=True), 256, 21),
-        # clustering with a cluster cap, no normalisation, refit every 2nd iteration, two shells
-        "shell3_n96_clustered_cap": (
-            UniformPrior(-6.0, 6.0, 3), TwinShells(3),
-            dict(n_dim=3, n_particles=96, clustering=True, normalize=False, cluster_every=2,
-                 n_max_clusters=3, split_threshold=0.5), 256, 22),
+        # clustering with a cluster cap (core.py:59-69), a lower split threshold, refit every 2nd iteration
+        "mix3_n96_clustered_cap": (
+            UniformPrior(-10.0, 10.0, 3), IsotropicMixture.four_corners(3),
+            dict(n_dim=3, n_particles=96, clustering=True, cluster_every=2, n_max_clusters=3,
+                 split_threshold=0.5), 256, 22),
     }
 
 

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libtempest_b200.so")
-SOURCES = ["tb_reweight.cu", "tb_resample.cu", "tb_moments.cu", "tb_linalg.cu", "tb_mcmc.cu"]
+SOURCES = ["tb_reweight.cu", "tb_resample.cu", "tb_moments.cu", "tb_linalg.cu", "tb_mcmc.cu", "tb_cluster.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-warn-spills",

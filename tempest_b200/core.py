@@ -62,6 +62,20 @@ class SamplerCore:
         for j in (config.reflective or []):
             kinds[j] = 2
         self._bc = torch.as_tensor(kinds).to(self.device) if kinds.any() else None
+        self.clusterer = None
+        self.assign = None                                     # int32 device labels of the active walkers
+        if config.clustering:                                  # core.py:54-69
+            if self.comm.on:
+                raise NotImplementedError("clustering=True is not sharded yet; run it on one GPU or pass "
+                                          "clustering=False (SURVEY 8e)")
+            from .cluster import HierarchicalGaussianMixture
+
+            cap = config.n_max_clusters
+            self.clusterer = HierarchicalGaussianMixture(
+                self.k, n_init=1, max_iterations=1000 if cap is None else cap - 1,
+                min_points=None if cap is None else 4 * config.n_dim,
+                threshold_modifier=config.split_threshold, covariance_type="full", verbose=False,
+                normalize=config.normalize)
         self.reweighter = Reweighter(self)
         self.trainer = Trainer(self)
         self.resampler = Resampler(self)
@@ -79,10 +93,6 @@ class SamplerCore:
                 "the fused CUDA path evaluates registry priors/likelihoods in-kernel "
                 "(tempest_b200.registry: UniformPrior, Rosenbrock, GaussianLikelihood, IsotropicMixture, "
                 "TwinShells); arbitrary Python callables are a later row (SURVEY 8f-3)")
-        if cfg.clustering:
-            raise NotImplementedError(
-                "clustering=True (hierarchical Gaussian mixture, cluster.py) is not built yet (SURVEY 8f-2); "
-                "pass clustering=False")
         if cfg.pool is not None:
             raise NotImplementedError("pool is meaningless on the vectorised CUDA path")
         if like.n_dim != cfg.n_dim or cfg.prior_transform.n_dim != cfg.n_dim:

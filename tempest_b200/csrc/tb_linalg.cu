@@ -3,34 +3,10 @@
 //   ref: tempest/modes.py:105-119 (ModeStatistics.__init__), tempest/student.py:75-79,
 //        tempest/tools.py:101-110 (volume_variation regularisation / inverse)
 #include "tb_common.cuh"
+#include "tb_chol.cuh"
 
 namespace {
 using namespace tb;
-
-// in-place lower Cholesky of the d x d matrix in `A` (shared memory); returns false on a
-// non-positive / non-finite pivot (LAPACK potrf info > 0  <=>  np.linalg.LinAlgError)
-__device__ bool chol_lower(double* A, int d) {
-  __shared__ int ok;
-  if (threadIdx.x == 0) ok = 1;
-  __syncthreads();
-  for (int j = 0; j < d; ++j) {
-    if (threadIdx.x == 0) {
-      double s = A[j * d + j];
-      for (int k = 0; k < j; ++k) s -= A[j * d + k] * A[j * d + k];
-      if (!(s > 0.0) || !isfinite(s)) ok = 0; else A[j * d + j] = sqrt(s);
-    }
-    __syncthreads();
-    if (!ok) return false;
-    const double piv = A[j * d + j];
-    for (int i = j + 1 + threadIdx.x; i < d; i += blockDim.x) {
-      double s = A[i * d + j];
-      for (int k = 0; k < j; ++k) s -= A[i * d + k] * A[j * d + k];
-      A[i * d + j] = s / piv;
-    }
-    __syncthreads();
-  }
-  return true;
-}
 
 __global__ void __launch_bounds__(128)
 chol_inv_kernel(double* __restrict__ a, int d, double* __restrict__ chol, double* __restrict__ inv,
@@ -61,16 +37,7 @@ chol_inv_kernel(double* __restrict__ a, int d, double* __restrict__ chol, double
   for (int e = threadIdx.x; e < d * d; e += blockDim.x) { int i = e / d, j = e - i * d; if (j > i) A[e] = 0.0; }
   __syncthreads();
   if (chol) for (int e = threadIdx.x; e < d * d; e += blockDim.x) chol[(size_t)blockIdx.x * d * d + e] = A[e];
-  // L^{-1}: column c by forward substitution, one column per thread
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    for (int i = 0; i < d; ++i) {
-      if (i < c) { Li[i * d + c] = 0.0; continue; }
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = c; k < i; ++k) s -= A[i * d + k] * Li[k * d + c];
-      Li[i * d + c] = s / A[i * d + i];
-    }
-  }
-  __syncthreads();
+  lower_inverse(A, Li, d);
   // inv = L^{-T} L^{-1}
   double fro_inv = 0.0, fro_a = 0.0;
   for (int e = threadIdx.x; e < d * d; e += blockDim.x) {

@@ -557,7 +557,7 @@ class Reweighter:
 
 
 class Trainer:
-    """steps/train.py:65-127 (global, clustering=False branch) + modes.py:221-288 + student.py:6-116."""
+    """steps/train.py:65-127 + modes.py:131-288 + student.py:6-116."""
 
     def __init__(self, core):
         self.core = core
@@ -578,13 +578,71 @@ class Trainer:
         n_trim = int(idx.numel())                       # local; equals the global count on one GPU
         n_trim_glob = int(k.last_trim["n_trim"])
         m_total = 4 * n_trim_glob
-        # modes.py:266-275: renormalise, draw 4n rows with replacement
+        if core.config.clustering:
+            return self._clustered(idx, wt, n_trim)
+        # modes.py:266: renormalise the trimmed weights
         if n_trim or not k.sharded:
             k.g_normalize(wt, n_trim)
         elif k.sharded:
             k.g_sum3(wt, 0, 0.0)                        # keep the collective sequence aligned across ranks
         draws = core.rng.train_u(m_total)
-        didx = k.ws.i64("train_didx", m_total)
+        mean, cov, chol, inv = self._fit_mode(idx, wt, n_trim, n_trim_glob, draws, "train_draw_idx")
+        dof = torch.full((1,), DOF_FALLBACK, dtype=F64, device=core.device)
+        return ModeStats(mean, cov, chol, inv, dof)
+
+    def _clustered(self, idx: torch.Tensor, wt: torch.Tensor, n_trim: int) -> ModeStats:
+        """train.py:97-115: (re)fit the hierarchy on the trimmed set, label it, and fit one Student-t
+        mode per distinct predicted label (modes.py:131-219)."""
+        core = self.core
+        ens = core.ensemble
+        k = core.k
+        cfg = core.config
+        d = ens.n_dim
+        it = int(core.state.raw("iter"))
+        core._stage("train:cluster")
+        if it % cfg.cluster_every == 0 or it == 0:                  # train.py:97-104
+            core.clusterer.fit(ens.u, wt, rows=idx)
+        labels = core.clusterer.predict(ens.u, rows=idx)           # train.py:101 / 112
+        core.trace["train_labels"] = labels
+        core._stage("train:modes")
+        k.g_normalize(wt, n_trim)                                  # modes.py:183
+        present = torch.unique(labels).cpu().numpy()               # modes.py:188 (sorted distinct labels)
+        draws = core.rng.train_u(4 * n_trim)
+        means, covs, chols, invs = [], [], [], []
+        offset = 0
+        draw_idx = []
+        for label in present:
+            pos = torch.nonzero(labels == int(label)).reshape(-1)  # modes.py:191, member order kept
+            n_c = int(pos.numel())
+            rows_c = idx[pos]
+            wt_c = torch.empty(n_c, dtype=F64, device=core.device)
+            _lib.check(k.lib.tb_take(ptr(wt), ptr(pos), n_c, ptr(wt_c), stream_ptr()), "tb_take")
+            k.g_normalize(wt_c, n_c)                               # modes.py:193-194
+            mean, cov, chol, inv = self._fit_mode(rows_c, wt_c, n_c, n_c, draws[offset: offset + 4 * n_c], None)
+            draw_idx.append(core.trace.get("_last_draw_idx"))
+            offset += 4 * n_c
+            means.append(mean)
+            covs.append(cov)
+            chols.append(chol)
+            invs.append(inv)
+        core.trace["train_draw_idx"] = draw_idx
+        K = len(present)
+        dof = torch.full((K,), DOF_FALLBACK, dtype=F64, device=core.device)
+        return ModeStats(torch.cat(means), torch.cat(covs), torch.cat(chols), torch.cat(invs), dof)
+
+    def _fit_mode(self, idx: torch.Tensor, wt: torch.Tensor, n_trim: int, n_trim_glob: int, draws: torch.Tensor,
+                  trace_key: Optional[str]):
+        """modes.py:197-209 / 272-282 for one mode: 4n weighted draws of the rows ``idx`` (normalised
+        weights ``wt``), then the Student-t fit of student.py:62-94 (median, Sigma, nu = inf)."""
+        core = self.core
+        ens = core.ensemble
+        d = ens.n_dim
+        k = core.k
+        lib = k.lib
+        st = stream_ptr()
+        m_total = 4 * n_trim_glob
+        didx = k.ws.i64("train_didx", m_total) if trace_key else torch.empty(m_total, dtype=torch.int64,
+                                                                              device=core.device)
         if k.sharded:
             # segments of the trimmed set per generation (trim indices are ascending = generation-major)
             seg_begin = torch.searchsorted(idx, core.generation_bounds())
@@ -594,7 +652,10 @@ class Trainer:
             k.search_right(cdf, n_trim, draws, didx)
         counts = k.ws.i32("train_counts", max(n_trim, 1))
         _lib.check(lib.tb_count_indices(ptr(didx), m_total, ptr(counts), max(n_trim, 1), st), "tb_count_indices")
-        core.trace["train_draw_idx"] = didx
+        if trace_key:
+            core.trace[trace_key] = didx
+        else:
+            core.trace["_last_draw_idx"] = didx
         # student.py:62: per-dimension median of the 4n-row multiset (even count: mean of the middle pair)
         core._stage("train:median")
         pair = k.ws.f64("train_pair", 2 * d)
@@ -629,8 +690,7 @@ class Trainer:
         inv = torch.empty((1, d, d), dtype=F64, device=core.device)
         info = k.ws.i32("train_info", 1)
         _lib.check(lib.tb_chol_inv(ptr(cov), d, 1, ptr(chol), ptr(inv), ptr(info), None, st), "tb_chol_inv")
-        dof = torch.full((1,), DOF_FALLBACK, dtype=F64, device=core.device)
-        return ModeStats(mean, cov, chol, inv, dof)
+        return mean, cov, chol, inv
 
 
 class Resampler:
@@ -667,7 +727,14 @@ class Resampler:
         logl = torch.empty(n, dtype=F64, device=core.device)
         _lib.check(k.lib.tb_gather_rows(ptr(ens.u), ptr(ens.logl), ens.n_dim, ptr(idx), n, ptr(u), ptr(logl),
                                         stream_ptr()), "tb_gather_rows")
-        st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
+        if core.config.clustering:                     # resample.py:92-94
+            assign = core.clusterer.predict(u)
+            core.assign = assign
+            core.trace["assignments"] = assign
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": assign})
+        else:
+            core.assign = None
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
 
 
 class Mutator:
@@ -715,10 +782,15 @@ class Mutator:
         u = st.raw("u")
         logl = st.raw("logl")
         K = mode_stats.K
+        assign = core.assign if cfg.clustering else None
+        if assign is not None and int(assign.max().item()) >= K:
+            # modes.py:188: modes are the distinct labels of the trimmed set; a walker labelled beyond
+            # them indexes past the mode arrays in the reference too (mcmc.py:228-231)
+            raise IndexError(f"walker assigned to cluster {int(assign.max().item())} but only {K} modes were fitted")
         ctrl = k.ws.f64("mcmc_ctrl", int(lib.tb_mcmc_ctrl_doubles(K)))
         ws = k.ws.bytes("mcmc_ws", lib.tb_mcmc_workspace_bytes(n, K))
         qcur = k.ws.f64("mcmc_q", n)
-        _lib.check(lib.tb_mcmc_begin(n, C.byref(params), None, ptr(u), ptr(qcur), ptr(ws), ptr(ctrl), sp),
+        _lib.check(lib.tb_mcmc_begin(n, C.byref(params), ptr(assign), ptr(u), ptr(qcur), ptr(ws), ptr(ctrl), sp),
                    "tb_mcmc_begin")
         tape = core.rng.mcmc_tape(n, d)
         tape_ref = C.byref(tape) if tape is not None else None
@@ -741,7 +813,7 @@ class Mutator:
             if tape is not None:
                 budget = min(budget, tape.steps - launched)
             if budget > 0:
-                _lib.check(lib.tb_mcmc_steps(n, C.byref(params), tape_ref, None, ptr(u), ptr(logl), ptr(qcur),
+                _lib.check(lib.tb_mcmc_steps(n, C.byref(params), tape_ref, ptr(assign), ptr(u), ptr(logl), ptr(qcur),
                                              ptr(ws), ptr(ctrl), int(budget), sp), "tb_mcmc_steps")
                 launched += budget
             h = ctrl.cpu().numpy()

@@ -5,12 +5,15 @@ relative (north-star tolerance) for fp64 reductions whose summation order differ
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
+
+from conftest import GOLDEN  # noqa: E402
 
 RTOL = 1e-10  # BASELINE.json north_star: "within 1e-10 relative in fp64"
 
@@ -406,3 +409,69 @@ def test_unit_median_pair_exact(env, n, d, width):
         env.k.g_select_pair(du, dr, d, rows.size, d, dm, r, False, out)
     np.testing.assert_array_equal(out.cpu().numpy().reshape(d, 2), np.stack([srt[r], srt[r + 1]], axis=1))
     assert np.array_equal(np.median(np.repeat(u[rows], mult, axis=0), axis=0), out.cpu().numpy().reshape(d, 2).mean(1))
+
+
+# ---- hierarchical Gaussian-mixture clustering (cluster.py) against the oracle --------------------------
+def _cluster_cases():
+    from oracle.gen_golden import cluster_cases
+
+    return cluster_cases()
+
+
+@pytest.mark.parametrize("name", ["cluster_blobs2d", "cluster_blobs5d", "cluster_single10d", "cluster_raw3d_cap",
+                                  "cluster_thin2d"])
+def test_hierarchical_mixture_matches_oracle(env, name):
+    from oracle import cluster_oracle as co
+    from oracle import ps_oracle as po
+    from tempest_b200.cluster import HierarchicalGaussianMixture, _Cluster
+
+    x, w, kw = _cluster_cases()[name]
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ref = co.fit_hierarchy(x, w, po.LegacyStream(0), **kw)
+    k = env.k
+    xd, wd = dev_arr(env, x), dev_arr(env, w)
+    h = HierarchicalGaussianMixture(k, **kw).fit(xd, wd)
+    assert h.n_clusters_ == ref.n_clusters == int(g["n_clusters"])
+    np.testing.assert_array_equal(h.labels_.cpu().numpy(), g["labels"])
+    np.testing.assert_allclose(np.array(h.cluster_centers_), g["centres"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(np.array(h.cluster_covariances_), g["covs"], rtol=1e-7, atol=1e-15)
+    np.testing.assert_allclose(h.cluster_weights_, g["weights"], rtol=1e-12)
+    np.testing.assert_array_equal(h.predict(dev_arr(env, g["y"])).cpu().numpy(), g["predict_y"])
+    np.testing.assert_array_equal(h.predict(xd).cpu().numpy(), g["predict_x"])
+    # the same fit through a row list (the trimmed-set form the sampler uses)
+    perm = np.random.RandomState(1).permutation(len(x))
+    big = np.zeros((len(x) + 7, x.shape[1]))
+    big[perm] = x
+    rows = dev_arr(env, perm.astype(np.int64), torch.int64)
+    h2 = HierarchicalGaussianMixture(k, **kw).fit(dev_arr(env, big), wd, rows=rows)
+    np.testing.assert_array_equal(h2.labels_.cpu().numpy(), g["labels"])
+    # single mixtures: EM iteration counts, BIC and parameters (cluster.py:56-133, 310-340)
+    hh = HierarchicalGaussianMixture(k, normalize=False)
+    xn = xd.contiguous()
+    cl = _Cluster(None, len(x))
+    hh._weights_of(cl, wd)
+    for comps in (1, 2):
+        fit = hh._fit_mixture(xn, cl, comps, x.shape[1])
+        assert fit.n_iter == int(g[f"gmm{comps}_n_iter"])
+        assert fit.bic() == pytest.approx(float(g[f"gmm{comps}_bic"]), rel=1e-9)
+        wts, means, covs = fit.host_params()
+        np.testing.assert_allclose(wts, g[f"gmm{comps}_weights"], rtol=1e-8)
+        np.testing.assert_allclose(means, g[f"gmm{comps}_means"], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(covs, g[f"gmm{comps}_covs"], rtol=1e-6, atol=1e-14)
+
+
+def test_split_by_label_keeps_order(env):
+    rs = np.random.RandomState(4)
+    for n in (1, 5, 2048, 2049, 100_003):
+        labels = (rs.rand(n) < 0.37).astype(np.int32)
+        members = np.sort(rs.choice(10 * n, n, replace=False)).astype(np.int64)
+        ld, md = dev_arr(env, labels, torch.int32), dev_arr(env, members, torch.int64)
+        zero = torch.empty(n, dtype=torch.int64, device=env.dev)
+        one = torch.empty(n, dtype=torch.int64, device=env.dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=env.dev)
+        ws = torch.zeros(env.lib.tb_split_workspace_bytes(n) + 64, dtype=torch.uint8, device=env.dev)
+        assert env.lib.tb_split_by_label(env.ptr(ld), env.ptr(md), n, env.ptr(ws), env.ptr(zero), env.ptr(one),
+                                         env.ptr(cnt), env.sp()) == 0
+        c1 = int(cnt.item())
+        np.testing.assert_array_equal(one[:c1].cpu().numpy(), members[labels != 0])
+        np.testing.assert_array_equal(zero[:n - c1].cpu().numpy(), members[labels == 0])

@@ -47,8 +47,7 @@ def run_pair(name, max_iterations=None):
     from tempest_b200.rng import TapeSource
 
     prior, like, kw, n_total, seed = cases()[name]
-    okw = {k: v for k, v in kw.items() if k != "clustering"}
-    o = po.OraclePS(prior, like, stream=po.LegacyStream(seed), record=True, **okw)
+    o = po.OraclePS(prior, like, stream=po.LegacyStream(seed), record=True, **kw)
     o.run(n_total, max_iterations=max_iterations)
     s = tp.Sampler(prior, like, vectorize=True, **kw)
     core = s._core
@@ -60,6 +59,14 @@ def run_pair(name, max_iterations=None):
     while core._not_termination():
         core.execute_iteration()
         tr = {key: (v.cpu().numpy() if hasattr(v, "cpu") else v) for key, v in core.trace.items()}
+        for key, v in tr.items():
+            if isinstance(v, list):
+                tr[key] = [e.cpu().numpy() if hasattr(e, "cpu") else e for e in v]
+        if core.clusterer is not None and core.clusterer.n_clusters_:
+            tr["n_clusters"] = core.clusterer.n_clusters_
+            tr["cluster_centres"] = np.array(core.clusterer.cluster_centers_)
+            tr["cluster_covs"] = np.array(core.clusterer.cluster_covariances_)
+            tr["cluster_weights"] = np.array(core.clusterer.cluster_weights_)
         tr["probe_log"] = list(core.reweighter.probe_log)
         tr["mode_mean"] = core.last_mode_stats.means.cpu().numpy()
         tr["mode_cov"] = core.last_mode_stats.covariances.cpu().numpy()
@@ -124,6 +131,47 @@ def test_full_run_matches_oracle_on_tapes(name):
     assert s.evidence()[0] == pytest.approx(float(g["final_logz"]), rel=RTOL)
     np.testing.assert_array_equal(st.get_history("beta"), g["h_beta"])
     np.testing.assert_array_equal(st.get_history("steps"), g["h_steps"])
+
+
+@pytest.mark.parametrize("name", ["mix2_n64_clustered", "mix3_n96_clustered_cap"])
+def test_clustered_run_matches_oracle_on_tapes(name):
+    """clustering=True: hierarchical mixture fits on the device (csrc/tb_cluster.cu) must find the same
+    clusters, labels and walker assignments as the oracle (pinned bit-exact to the reference), and
+    the multi-mode MCMC must then take the same steps."""
+    o, s, traces = run_pair(name)
+    st = s.state
+    assert st.get_history_length() == len(o.hist["beta"])
+    np.testing.assert_array_equal(st.get_history("beta"), np.array(o.hist["beta"]))
+    np.testing.assert_array_equal(st.get_history("steps"), np.array(o.hist["steps"]))
+    np.testing.assert_array_equal(st.get_history("calls"), np.array(o.hist["calls"]))
+    seen_multi = False
+    for t, (tr, otr) in enumerate(zip(traces, o.traces)):
+        if "train_labels" not in otr:
+            continue
+        assert tr["n_clusters"] == otr["n_clusters"], f"cluster count @ iteration {t}"
+        seen_multi |= otr["n_clusters"] > 1
+        np.testing.assert_array_equal(tr["trim_idx"], otr["trim_idx"], err_msg=f"trim @ {t}")
+        np.testing.assert_array_equal(tr["train_labels"], otr["train_labels"], err_msg=f"labels @ {t}")
+        np.testing.assert_allclose(tr["cluster_centres"], otr["cluster_centres"], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(tr["cluster_covs"], otr["cluster_covs"], rtol=1e-7, atol=1e-14)
+        np.testing.assert_allclose(tr["cluster_weights"], otr["cluster_weights"], rtol=1e-10)
+        assert len(tr["train_draw_idx"]) == len(otr["train_draw_idx"])
+        for a, b in zip(tr["train_draw_idx"], otr["train_draw_idx"]):
+            np.testing.assert_array_equal(a, b, err_msg=f"mode draws @ {t}")
+        np.testing.assert_array_equal(tr["resample_idx"], otr["resample_idx"], err_msg=f"resample @ {t}")
+        np.testing.assert_array_equal(tr["assignments"], otr["assignments"], err_msg=f"assignments @ {t}")
+        np.testing.assert_allclose(tr["mode_mean"], otr["mode_mean"], rtol=1e-12)
+        np.testing.assert_allclose(tr["mode_cov"], otr["mode_cov"], rtol=1e-9, atol=1e-14)
+    assert seen_multi, "the case never produced more than one cluster: it does not exercise the hierarchy"
+    np.testing.assert_allclose(st.get_history("logz"), np.array(o.hist["logz"]), rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(st.get_history("acceptance"), np.array(o.hist["acceptance"]), rtol=RTOL)
+    np.testing.assert_allclose(st.get_history("efficiency"), np.array(o.hist["efficiency"]), rtol=RTOL)
+    du = np.abs(st.get_history("u") - np.array(o.hist["u"])).max()
+    assert du < 1e-12, f"walker positions differ by {du}: an accept/reject decision flipped"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    np.testing.assert_array_equal(st.get_history("beta"), g["h_beta"])
+    np.testing.assert_array_equal(st.get_history("steps"), g["h_steps"])
+    assert s.evidence()[0] == pytest.approx(float(g["final_logz"]), rel=RTOL)
 
 
 def test_generic_step_kernel_matches_oracle_on_tapes():
