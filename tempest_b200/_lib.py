@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtempest_b200.so")
+LIB_PATH = os.environ.get("TEMPEST_B200_LIB") or os.path.join(_HERE, "lib", "libtempest_b200.so")
 
 c_i32, c_i64, c_u32, c_u64, c_f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
 PTR = C.c_void_p

@@ -13,13 +13,13 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libtempest_b200.so")
+OBJDIR = os.path.join(HERE, "build" + os.environ.get("TB_OBJ_SUFFIX", ""))
+LIB = os.path.join(LIBDIR, os.environ.get("TB_LIB_NAME", "libtempest_b200.so"))   # TB_LIB_NAME / TB_NVCC_EXTRA: A/B builds
 SOURCES = ["tb_reweight.cu", "tb_resample.cu", "tb_moments.cu", "tb_linalg.cu", "tb_mcmc.cu", "tb_cluster.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-warn-spills",
-]
+] + os.environ.get("TB_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -153,15 +153,22 @@ __device__ void apply_step_update(const tb_mcmc_params& p, double* ctrl, const d
 // recorded fp64 variates instead and is bit-compatible with the generic kernel.
 __device__ __forceinline__ void bm_pair32(uint32_t a, uint32_t b, double& z0, double& z1) {
   const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;   // (0,1]
-  const float r = sqrtf(-2.0f * logf(u1));
+  // MUFU-based log / sin / cos (abs. error ~2^-21 on [-pi, pi]): 5-7 % faster steps than logf / sincospif,
+  // and far below the fp32 resolution the proposal noise already has
+  const float r = __fsqrt_rn(-2.0f * __logf(u1));
   float s, c;
-  sincospif((float)b * 4.656612873077393e-10f, &s, &c);            // 2*pi*b/2^32
+  __sincosf(((float)(int32_t)b) * 1.4629180792671596e-9f, &s, &c);  // angle in [-pi, pi): 2*pi*b/2^32 (signed)
   z0 = (double)(r * c);
   z1 = (double)(r * s);
 }
 
+// resident CTAs per SM the register allocation is held to (measured at D = 10: 6 CTAs / 80 registers
+// beat 5 CTAs / 96 registers by ~3 %)
+template <int D>
+constexpr int mcmc_min_ctas() { return D <= 10 ? 6 : (D <= 12 ? 4 : 3); }
+
 template <int D, bool TPCN, bool TAPE>
-__global__ void __launch_bounds__(kMcmcBlock)
+__global__ void __launch_bounds__(kMcmcBlock, mcmc_min_ctas<D>())
 mcmc_step_fast(StepArgs a) {
   if (a.ctrl[C_DONE] != 0.0) return;
   constexpr int B = kMcmcBlock;
