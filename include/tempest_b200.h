@@ -30,7 +30,7 @@ enum {
 };
 
 /* likelihood / prior kernel ids (tempest_b200/registry.py) */
-enum { TB_LIKE_ROSENBROCK = 0, TB_LIKE_GAUSSIAN = 1, TB_LIKE_ISO_MIXTURE = 2, TB_LIKE_TWIN_SHELLS = 3 };
+enum { TB_LIKE_EXTERNAL = -1, TB_LIKE_ROSENBROCK = 0, TB_LIKE_GAUSSIAN = 1, TB_LIKE_ISO_MIXTURE = 2, TB_LIKE_TWIN_SHELLS = 3 };
 enum { TB_PRIOR_AFFINE = 0 };
 enum { TB_SAMPLE_TPCN = 0, TB_SAMPLE_RWM = 1 };
 enum { TB_RNG_PHILOX = 0, TB_RNG_TAPE = 1 };
@@ -291,6 +291,17 @@ int tb_moments_partial(const double* u, const int64_t* rows, const double* w, co
 int tb_next_beta_x(const double* logl, const double* C, int64_t n_total, double beta_prev,
                    double ess_target, int32_t flags, void* workspace, double* result16,
                    double* probe_log, int32_t probe_log_cap, const tb_xgpu* xgpu, tb_stream_t stream);
+/* One Metropolis step split around a CALLER-evaluated likelihood (arbitrary prior_transform /
+ * log_likelihood callables, core.py:317-358): tb_mcmc_propose writes the in-cube proposals u_prop[n][d]
+ * and meta[n] (proposals drawn, or -error); the caller computes logl_prop = L(prior(u_prop)); then
+ * tb_mcmc_accept does the Student-t ratio, accept/reject, sigma adaptation and the stop rule exactly
+ * like tb_mcmc_steps.  Set like_id = TB_LIKE_EXTERNAL in tb_mcmc_begin's params. */
+int tb_mcmc_propose(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign,
+                    const double* u, const double* logl, const double* qcur, void* workspace, double* ctrl,
+                    double* u_prop, int32_t* meta, tb_stream_t stream);
+int tb_mcmc_accept(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign,
+                   double* u, double* logl, double* qcur, void* workspace, double* ctrl,
+                   const double* u_prop, const double* logl_prop, const int32_t* meta, tb_stream_t stream);
 /* apply sigma adaptation + stop rule from all-reduced per-step totals (defer_update = 1) */
 int tb_mcmc_update(const tb_mcmc_params* p, double* ctrl, tb_stream_t stream);
 

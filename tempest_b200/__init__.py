@@ -14,6 +14,12 @@ from .registry import (GaussianLikelihood, IsotropicMixture, Rosenbrock, TwinShe
 __version__ = "0.1.0"
 
 
+def device_callable(fn):
+    """Mark a prior_transform / log_likelihood as operating on CUDA fp64 torch tensors (callables.py)."""
+    fn._tb_device = True
+    return fn
+
+
 def __getattr__(name):
     if name == "Sampler":
         from .sampler import Sampler

@@ -52,10 +52,20 @@ class SamplerCore:
         self.n_total = 0
         self.logz_err = None
         self._weights = None
-        like = config.log_likelihood.f if hasattr(config.log_likelihood, "f") else config.log_likelihood
+        # registry objects run inside the fused step kernel; anything else goes through the split step
+        # (tb_mcmc_propose -> callables -> tb_mcmc_accept), see callables.py
+        from .callables import CallableBridge
+
+        self.bridge = CallableBridge(config, self.device)
+        if self.bridge.external and self.comm.on:
+            raise NotImplementedError("arbitrary callables are single-GPU for now; registry priors/likelihoods shard")
+        like = self.bridge.like_inner
         self._like = like
-        self._like_params = torch.as_tensor(like.dparams(), dtype=F64).to(self.device)
-        self._prior_params = torch.as_tensor(config.prior_transform.dparams(), dtype=F64).to(self.device)
+        self._like_id = like.kernel_id if self.bridge.like_registry else -1
+        self._like_params = (torch.as_tensor(like.dparams(), dtype=F64).to(self.device)
+                             if self.bridge.like_registry else None)
+        self._prior_params = (torch.as_tensor(config.prior_transform.dparams(), dtype=F64).to(self.device)
+                              if self.bridge.prior_registry else None)
         kinds = np.zeros(config.n_dim, dtype=np.uint8)
         for j in (config.periodic or []):
             kinds[j] = 1
@@ -84,19 +94,14 @@ class SamplerCore:
     # -- what the CUDA path supports ----------------------------------------------------------
     @staticmethod
     def _check_supported(cfg: SamplerConfig) -> None:
-        if not cfg.vectorize:
-            raise NotImplementedError(
-                "tempest_b200 implements the vectorize=True path only (no per-sample pool.map, core.py:323-326)")
-        like = cfg.log_likelihood.f if hasattr(cfg.log_likelihood, "f") else cfg.log_likelihood
-        if not is_registry_likelihood(like) or not is_registry_prior(cfg.prior_transform):
-            raise NotImplementedError(
-                "the fused CUDA path evaluates registry priors/likelihoods in-kernel "
-                "(tempest_b200.registry: UniformPrior, Rosenbrock, GaussianLikelihood, IsotropicMixture, "
-                "TwinShells); arbitrary Python callables are a later row (SURVEY 8f-3)")
+        if cfg.blobs_dtype is not None:
+            raise NotImplementedError("blobs are not carried by the device ensemble (state_manager.py blobs)")
         if cfg.pool is not None:
             raise NotImplementedError("pool is meaningless on the vectorised CUDA path")
-        if like.n_dim != cfg.n_dim or cfg.prior_transform.n_dim != cfg.n_dim:
-            raise ValueError("registry prior / likelihood dimension does not match n_dim")
+        like = cfg.log_likelihood.f if hasattr(cfg.log_likelihood, "f") else cfg.log_likelihood
+        for obj, ok in ((like, is_registry_likelihood(like)), (cfg.prior_transform, is_registry_prior(cfg.prior_transform))):
+            if ok and obj.n_dim != cfg.n_dim:
+                raise ValueError("registry prior / likelihood dimension does not match n_dim")
 
     # -- helpers used by the steps ---------------------------------------------------------------
     @property
@@ -122,8 +127,8 @@ class SamplerCore:
         p.n_modes = mode_stats.K if mode_stats is not None else 1
         p.sampler = 1 if cfg.sample == "rwm" else 0
         p.rng_mode = self.rng.mode
-        p.like_id = self._like.kernel_id
-        p.prior_id = cfg.prior_transform.kernel_id
+        p.like_id = self._like_id
+        p.prior_id = cfg.prior_transform.kernel_id if self.bridge.prior_registry else -1
         p.n_steps = cfg.n_steps
         p.n_max = cfg.n_max_steps
         p.beta = float(beta)
@@ -132,8 +137,8 @@ class SamplerCore:
         p.slot_offset = self.slot_offset
         p.n_global = self.n_global
         p.defer_update = 1 if self.comm.on else 0
-        p.like_params = self._like_params.data_ptr()
-        p.prior_params = self._prior_params.data_ptr()
+        p.like_params = self._like_params.data_ptr() if self._like_params is not None else None
+        p.prior_params = self._prior_params.data_ptr() if self._prior_params is not None else None
         if mode_stats is not None:
             p.mode_mean = mode_stats.means.data_ptr()
             p.mode_chol = mode_stats.chol_covariances.data_ptr()
@@ -143,7 +148,12 @@ class SamplerCore:
         return p
 
     def transform_to_x(self, u: torch.Tensor) -> torch.Tensor:
-        """x = prior_transform(u) on the device (tb_transform)."""
+        """x = prior_transform(u): tb_transform for registry priors, the user's callable otherwise."""
+        if not self.bridge.prior_registry:
+            return self.bridge.prior(u, self) if int(u.shape[0]) else torch.empty_like(u)
+        return self.registry_transform(u)
+
+    def registry_transform(self, u: torch.Tensor) -> torch.Tensor:
         n = int(u.shape[0])
         x = torch.empty_like(u)
         if n:

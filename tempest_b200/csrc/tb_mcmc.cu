@@ -43,6 +43,10 @@ struct StepArgs {
   McmcWs* ws;
   double* ctrl;
   tb_xgpu x;          // world > 1: the per-step totals are exchanged over peer memory inside the kernel
+  // split step for caller-evaluated likelihoods (tb_mcmc_propose / tb_mcmc_accept)
+  double* ext_prop;          // [n][d] proposals in the unit cube
+  const double* ext_logl;    // [n] log-likelihood of the proposals, filled by the caller
+  int32_t* ext_meta;         // [n] proposals drawn (> 0) or -error
 };
 
 __device__ __forceinline__ double bc_apply(double v, int kind) {
@@ -423,7 +427,9 @@ mcmc_step_fast(StepArgs a) {
   if (last_block_arrives(&a.ws->ticket)) finish_step(a, K, gridDim.x);
 }
 
-template <int DP>
+// PHASE 0: whole step with the in-kernel registry likelihood.  PHASE 1: proposal only (written to
+// ext_prop / ext_meta).  PHASE 2: accept / reject against caller-evaluated ext_logl, sigma adaptation, stop rule.
+template <int DP, int PHASE>
 __global__ void __launch_bounds__(kMcmcBlock)
 mcmc_step_kernel(StepArgs a) {
   if (a.ctrl[C_DONE] != 0.0) return;
@@ -468,8 +474,14 @@ mcmc_step_kernel(StepArgs a) {
     if (tape && step >= a.tape.steps) err = 1;
 
     double scale_s = 0.0, q = 0.0, keep = 0.0;
-    if (tpcn) {
-      q = a.qcur[k];
+    if (tpcn) q = a.qcur[k];
+    if (PHASE == 2) {
+      const int meta = a.ext_meta[k];
+      if (meta > 0) nprop = meta; else err = -meta;
+#pragma unroll
+      for (int i = 0; i < DP; ++i) if (i < d) prop[i] = a.ext_prop[k * d + i];
+    }
+    if (tpcn && PHASE != 2) {
       // s = 1 / Gamma(shape=(d+nu)/2, scale=2/(nu+q))   (mcmc.py:233-236)
       double g;
       if (tape) g = err ? 1.0 : a.tape.gamma[tix];
@@ -498,7 +510,7 @@ mcmc_step_kernel(StepArgs a) {
     const double* ztape = tape && !err ? a.tape.z + a.tape.z_off[tix] : nullptr;
     bool inside = false;
     int attempt = 0;
-    while (!inside && !err) {
+    while (PHASE != 2 && !inside && !err) {
       if (tape) {
         if (attempt >= n_att_tape) { err = 1; break; }
 #pragma unroll
@@ -528,12 +540,20 @@ mcmc_step_kernel(StepArgs a) {
       ++attempt;
       if (attempt >= kMaxAttempts) { err = 2; break; }
     }
-    if (!err) {
-      // prior transform + likelihood in registers
-      double x[DP];
+    if (PHASE == 1) {
+      a.ext_meta[k] = err ? -err : nprop;
 #pragma unroll
-      for (int i = 0; i < DP; ++i) if (i < d) x[i] = prior_affine(a.p.prior_params, d, i, prop[i]);
-      const double logl_new = eval_like(a.p.like_id, a.p.like_params, d, x);
+      for (int i = 0; i < DP; ++i) if (i < d) a.ext_prop[k * d + i] = err ? u[i] : prop[i];
+    }
+    if (PHASE != 1 && !err) {
+      double logl_new;
+      if (PHASE == 2) logl_new = a.ext_logl[k];
+      else {   // prior transform + likelihood in registers
+        double x[DP];
+#pragma unroll
+        for (int i = 0; i < DP; ++i) if (i < d) x[i] = prior_affine(a.p.prior_params, d, i, prop[i]);
+        logl_new = eval_like(a.p.like_id, a.p.like_params, d, x);
+      }
       double factor = 0.0, q_new = 0.0;
       if (tpcn) {   // Student-t density ratio (mcmc.py:251-279)
         double dn[DP];
@@ -565,6 +585,7 @@ mcmc_step_kernel(StepArgs a) {
       }
     }
   }
+  if (PHASE == 1) return;
   // CTA partials: shared atomics would make the order run-dependent; use a fixed-order fold
   __shared__ double fold[kMcmcBlock];
   __shared__ int foldc[kMcmcBlock];
@@ -642,11 +663,14 @@ prior_draw_kernel(int64_t n, tb_mcmc_params p, const double* __restrict__ tape_u
     else if (tape_u) { a = tape_u[k * d + i]; if (i + 1 < d) b = tape_u[k * d + i + 1]; }
     else philox_u2(rng, slot, 0u, RNG_PRIOR, (uint32_t)(i / 2), a, b, false);
     if (u) u[k * d + i] = a;
-    xs[i] = prior_affine(p.prior_params, d, i, a);
-    if (i + 1 < d) { if (u) u[k * d + i + 1] = b; xs[i + 1] = prior_affine(p.prior_params, d, i + 1, b); }
+    if (i + 1 < d && u) u[k * d + i + 1] = b;
+    if (p.prior_params) {                      // NULL: caller-evaluated prior, only the uniforms are wanted
+      xs[i] = prior_affine(p.prior_params, d, i, a);
+      if (i + 1 < d) xs[i + 1] = prior_affine(p.prior_params, d, i + 1, b);
+    }
   }
-  if (x) for (int i = 0; i < d; ++i) x[k * d + i] = xs[i];
-  if (logl) logl[k] = eval_like(p.like_id, p.like_params, d, xs);
+  if (x && p.prior_params) for (int i = 0; i < d; ++i) x[k * d + i] = xs[i];
+  if (logl && p.prior_params && p.like_params && p.like_id >= 0) logl[k] = eval_like(p.like_id, p.like_params, d, xs);
 }
 
 // uniforms for the host-driven resampling / training draws (same Philox stream family)
@@ -662,18 +686,33 @@ philox_uniform_kernel(uint64_t seed, uint64_t iteration, uint32_t purpose, int64
   }
 }
 
-template <int DP>
+template <int DP, int PHASE>
 int launch_steps(const StepArgs& a, int count, cudaStream_t st) {
   const int d = a.p.n_dim, K = a.p.n_modes;
   const size_t smem = sizeof(double) * ((size_t)K * d + 2 * (size_t)K * d * d + 2 * K + K + 3);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(mcmc_step_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mcmc_step_kernel<DP, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
   const int grid = (int)((a.n + kMcmcBlock - 1) / kMcmcBlock);
-  for (int s = 0; s < count; ++s) mcmc_step_kernel<DP><<<grid, kMcmcBlock, smem, st>>>(a);
+  for (int s = 0; s < count; ++s) mcmc_step_kernel<DP, PHASE><<<grid, kMcmcBlock, smem, st>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? TB_OK : (int)e;
+}
+
+template <int PHASE>
+int launch_generic(const StepArgs& a, int count, cudaStream_t st) {
+  const int d = a.p.n_dim;
+  if (d <= 2) return launch_steps<2, PHASE>(a, count, st);
+  if (d <= 4) return launch_steps<4, PHASE>(a, count, st);
+  if (d <= 6) return launch_steps<6, PHASE>(a, count, st);
+  if (d <= 8) return launch_steps<8, PHASE>(a, count, st);
+  if (d <= 10) return launch_steps<10, PHASE>(a, count, st);
+  if (d <= 16) return launch_steps<16, PHASE>(a, count, st);
+  if (d <= 32) return launch_steps<32, PHASE>(a, count, st);
+  if (d <= 64) return launch_steps<64, PHASE>(a, count, st);
+  return launch_steps<128, PHASE>(a, count, st);
 }
 
 template <int D, bool TPCN, bool TAPE>
@@ -728,7 +767,8 @@ int tb_mcmc_update(const tb_mcmc_params* p, double* ctrl, tb_stream_t stream) {
 
 int tb_prior_draw(int64_t n, const tb_mcmc_params* p, const double* prior_u_tape, double* u, double* x,
                   double* logl, tb_stream_t stream) {
-  if (!params_ok(n, p) || !u) return TB_ERR_ARG;
+  if (!p || n <= 0 || p->n_dim <= 0 || p->n_dim > 128 || !u) return TB_ERR_ARG;
+  if ((x && !p->prior_params) || (logl && (!p->prior_params || !p->like_params || p->like_id < 0))) return TB_ERR_ARG;
   const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);
   prior_draw_kernel<<<grid, kMcmcBlock, 0, as_stream(stream)>>>(n, *p, prior_u_tape, nullptr, u, x, logl);
   TB_CHECK_LAUNCH();
@@ -736,7 +776,8 @@ int tb_prior_draw(int64_t n, const tb_mcmc_params* p, const double* prior_u_tape
 }
 
 int tb_transform(const double* u, int64_t n, const tb_mcmc_params* p, double* x, double* logl, tb_stream_t stream) {
-  if (!params_ok(n, p) || !u) return TB_ERR_ARG;
+  if (!p || n <= 0 || p->n_dim <= 0 || p->n_dim > 128 || !u || !p->prior_params) return TB_ERR_ARG;
+  if (logl && (!p->like_params || p->like_id < 0)) return TB_ERR_ARG;
   const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);
   prior_draw_kernel<<<grid, kMcmcBlock, 0, as_stream(stream)>>>(n, *p, nullptr, u, nullptr, x, logl);
   TB_CHECK_LAUNCH();
@@ -754,14 +795,18 @@ int tb_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t purpose, int64
 
 int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, const double* u, double* qcur,
                   void* workspace, double* ctrl, tb_stream_t stream) {
-  if (!params_ok(n, p) || !u || !workspace || !ctrl) return TB_ERR_ARG;
+  if (!p || n <= 0 || p->n_dim <= 0 || p->n_dim > 128 || p->n_modes <= 0 || p->n_modes > kMaxModes || !u || !workspace ||
+      !ctrl)
+    return TB_ERR_ARG;
   cudaStream_t st = as_stream(stream);
   cudaError_t e = cudaMemsetAsync(workspace, 0, 16, st);
   if (e != cudaSuccess) return (int)e;
   mcmc_init_ctrl_kernel<<<1, 256, 0, st>>>(*p, ctrl);
   const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);
   // the fast step kernel computes q itself on its first step
-  const bool need_q = p->sampler == TB_SAMPLE_TPCN && (tb_force_generic_mcmc || !has_fast_path(p->n_dim));
+  // (the generic and the split step kernels read it from qcur; like_id < 0 marks caller-evaluated likelihoods)
+  const bool need_q = p->sampler == TB_SAMPLE_TPCN &&
+                      (tb_force_generic_mcmc || !has_fast_path(p->n_dim) || p->like_id < 0);
   mcmc_begin_kernel<<<grid, kMcmcBlock, 0, st>>>(n, *p, assign, u, need_q ? qcur : nullptr, ctrl);
   TB_CHECK_LAUNCH();
   return TB_OK;
@@ -777,6 +822,7 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
   if (tape) a.tape = *tape; else { a.tape.gamma = nullptr; a.tape.acc_u = nullptr; a.tape.z = nullptr;
                                     a.tape.z_off = nullptr; a.tape.z_cnt = nullptr; a.tape.steps = 0; }
   a.assign = assign; a.u = u; a.logl = logl; a.qcur = qcur; a.ws = (McmcWs*)workspace; a.ctrl = ctrl;
+  a.ext_prop = nullptr; a.ext_logl = nullptr; a.ext_meta = nullptr;
   if (p->xgpu) {
     a.x = *p->xgpu;
     if (a.x.world < 1 || a.x.world > kXMaxRanks || a.x.seq < 1 || p->n_modes + 3 > 15) return TB_ERR_ARG;
@@ -799,15 +845,48 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
       default: break;
     }
   }
-  if (d <= 2) return launch_steps<2>(a, count, st);
-  if (d <= 4) return launch_steps<4>(a, count, st);
-  if (d <= 6) return launch_steps<6>(a, count, st);
-  if (d <= 8) return launch_steps<8>(a, count, st);
-  if (d <= 10) return launch_steps<10>(a, count, st);
-  if (d <= 16) return launch_steps<16>(a, count, st);
-  if (d <= 32) return launch_steps<32>(a, count, st);
-  if (d <= 64) return launch_steps<64>(a, count, st);
-  return launch_steps<128>(a, count, st);
+  return launch_generic<0>(a, count, st);
+}
+
+// one Metropolis step split around a caller-evaluated likelihood (arbitrary user callables):
+//   tb_mcmc_propose -> caller: x = prior(u_prop), logl_prop = L(x) -> tb_mcmc_accept
+static int split_args(StepArgs& a, int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign,
+                      double* u, double* logl, double* qcur, void* workspace, double* ctrl) {
+  if (!p || n <= 0 || p->n_dim <= 0 || p->n_dim > 128 || p->n_modes <= 0 || p->n_modes > kMaxModes || !u || !workspace ||
+      !ctrl)
+    return TB_ERR_ARG;
+  if (p->sampler == TB_SAMPLE_TPCN && !qcur) return TB_ERR_ARG;
+  if (p->rng_mode == TB_RNG_TAPE && !tape) return TB_ERR_ARG;
+  if (p->xgpu) return TB_ERR_ARG;             // the split step is single-GPU
+  a.n = n; a.p = *p;
+  if (tape) a.tape = *tape; else { a.tape.gamma = nullptr; a.tape.acc_u = nullptr; a.tape.z = nullptr;
+                                    a.tape.z_off = nullptr; a.tape.z_cnt = nullptr; a.tape.steps = 0; }
+  a.assign = assign; a.u = u; a.logl = logl; a.qcur = qcur; a.ws = (McmcWs*)workspace; a.ctrl = ctrl;
+  a.x.rank = 0; a.x.world = 1; a.x.seq = 1;
+  for (int i = 0; i < 8; ++i) a.x.peer[i] = nullptr;
+  return TB_OK;
+}
+
+int tb_mcmc_propose(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign, const double* u,
+                    const double* logl, const double* qcur, void* workspace, double* ctrl, double* u_prop,
+                    int32_t* meta, tb_stream_t stream) {
+  StepArgs a;
+  if (int rc = split_args(a, n, p, tape, assign, const_cast<double*>(u), const_cast<double*>(logl),
+                          const_cast<double*>(qcur), workspace, ctrl))
+    return rc;
+  if (!u_prop || !meta || !logl) return TB_ERR_ARG;
+  a.ext_prop = u_prop; a.ext_logl = nullptr; a.ext_meta = meta;
+  return launch_generic<1>(a, 1, as_stream(stream));
+}
+
+int tb_mcmc_accept(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign, double* u,
+                   double* logl, double* qcur, void* workspace, double* ctrl, const double* u_prop,
+                   const double* logl_prop, const int32_t* meta, tb_stream_t stream) {
+  StepArgs a;
+  if (int rc = split_args(a, n, p, tape, assign, u, logl, qcur, workspace, ctrl)) return rc;
+  if (!u_prop || !logl_prop || !meta || !logl) return TB_ERR_ARG;
+  a.ext_prop = const_cast<double*>(u_prop); a.ext_logl = logl_prop; a.ext_meta = const_cast<int32_t*>(meta);
+  return launch_generic<2>(a, 1, as_stream(stream));
 }
 
 }  // extern "C"

@@ -742,6 +742,37 @@ class Mutator:
 
     CHUNK = 8   # Metropolis steps enqueued between looks at the device-side stop flag
 
+    def _external_loop(self, params, tape, tape_ref, assign, u, logl, qcur, ws, ctrl, n_cap: int):
+        """Split Metropolis steps around the user's callables (mcmc.py:142-208): proposal kernel ->
+        x = prior_transform(u'), logl' = log_likelihood(x') -> accept kernel with sigma adaptation and
+        the stop rule.  Device callables are enqueued without a host round trip and the stop flag is read
+        every CHUNK steps; numpy callables synchronise every step anyway."""
+        core = self.core
+        k = core.k
+        lib = k.lib
+        sp = stream_ptr()
+        n, d = core.n_local, core.config.n_dim
+        u_prop = k.ws.f64("mcmc_u_prop", n * d).reshape(n, d)
+        meta = k.ws.i32("mcmc_meta", n)
+        on_device = (core.bridge.prior_registry or core.bridge.prior_device) and core.bridge.like_device
+        look_every = self.CHUNK if on_device else 1
+        launched = 0
+        while True:
+            if tape is not None and launched >= tape.steps:
+                raise RuntimeError(
+                    f"tape holds {tape.steps} MCMC steps but the device stop rule has not fired after {launched}")
+            _lib.check(lib.tb_mcmc_propose(n, C.byref(params), tape_ref, ptr(assign), ptr(u), ptr(logl), ptr(qcur),
+                                           ptr(ws), ptr(ctrl), ptr(u_prop), ptr(meta), sp), "tb_mcmc_propose")
+            logl_prop = core.bridge.like(core.bridge.prior(u_prop, core))
+            _lib.check(lib.tb_mcmc_accept(n, C.byref(params), tape_ref, ptr(assign), ptr(u), ptr(logl), ptr(qcur),
+                                          ptr(ws), ptr(ctrl), ptr(u_prop), ptr(logl_prop), ptr(meta), sp),
+                       "tb_mcmc_accept")
+            launched += 1
+            if launched % look_every == 0 or launched >= n_cap:
+                h = ctrl.cpu().numpy()
+                if h[1] != 0.0 or launched >= n_cap:
+                    return h, launched
+
     def __init__(self, core):
         self.core = core
 
@@ -759,8 +790,12 @@ class Mutator:
             u = torch.empty((n, d), dtype=F64, device=core.device)
             logl = torch.empty(n, dtype=F64, device=core.device)
             tape_u = core.rng.prior_u(n, d)
-            _lib.check(lib.tb_prior_draw(n, C.byref(params), ptr(tape_u), ptr(u), None, ptr(logl), sp),
-                       "tb_prior_draw")
+            if core.bridge.external:                   # same uniforms; prior / likelihood by the user's callables
+                _lib.check(lib.tb_prior_draw(n, C.byref(params), ptr(tape_u), ptr(u), None, None, sp), "tb_prior_draw")
+                logl = core.bridge.like(core.bridge.prior(u, core))
+            else:
+                _lib.check(lib.tb_prior_draw(n, C.byref(params), ptr(tape_u), ptr(u), None, ptr(logl), sp),
+                           "tb_prior_draw")
             st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int),
                                "calls": st.raw("calls") + core.n_global, "steps": 1, "acceptance": 1.0,
                                "efficiency": 1.0})
@@ -799,7 +834,9 @@ class Mutator:
         launched = 0
         budget = min(n_min, n_cap)
         fused = k.sharded and k.xgpu is not None and K + 3 <= 15
-        if k.sharded:
+        if core.bridge.external:
+            h, launched = self._external_loop(params, tape, tape_ref, assign, u, logl, qcur, ws, ctrl, n_cap)
+        elif k.sharded:
             k.comm.allreduce_sum_(ctrl[8 + K: 8 + 2 * K])          # walkers per mode: global counts
         if fused:
             params.xgpu = C.pointer(k.xgpu)                        # per-step all-reduce fused into the step kernel
@@ -809,7 +846,7 @@ class Mutator:
 
             h, launched = sharded_mcmc_loop(core, params, tape_ref, u, logl, qcur, ws, ctrl, min(n_min, n_cap),
                                             n_cap, self.CHUNK)
-        while fused or not k.sharded:
+        while (fused or not k.sharded) and not core.bridge.external:
             if tape is not None:
                 budget = min(budget, tape.steps - launched)
             if budget > 0:
@@ -824,7 +861,7 @@ class Mutator:
                     f"tape holds {tape.steps} MCMC steps but the device stop rule has not fired after {launched}")
             budget = min(self.CHUNK, n_cap - launched)
         core.n_mcmc_launches += launched
-        if fused:
+        if fused and not core.bridge.external:
             k.consume_exchanges(int(h[0]))                         # one exchange per executed step
         if h[4] != 0.0:
             raise RuntimeError(f"MCMC kernel error flag {h[4]} (1: tape exhausted, 2: proposal never entered the cube)")
