@@ -200,6 +200,10 @@ class SamplerCore:
         self._stage_events = []
 
     def execute_iteration(self, save_every=None, t0: int = 0, export: bool = True) -> dict:
+        if save_every is not None:                           # core.py:164-172
+            it = int(self.state.raw("iter") or 0)
+            if (it - t0) % int(save_every) == 0 and it != t0:
+                self.save_sampler_state(self.config.output_dir / f"{self.config.output_label}_{it}.state")
         self.trace = {}
         if getattr(self, "profile", False):
             self._stage_events = []
@@ -226,17 +230,21 @@ class SamplerCore:
 
     def run_sampling(self, n_total: int = 4096, progress: bool = True, resume_state_path=None,
                      save_every: Optional[int] = None) -> None:
-        if resume_state_path is not None or save_every is not None:
-            raise NotImplementedError("checkpoint/resume is outside the hot path (SURVEY 8f-4; upstream load is broken)")
-        self._initialize_fresh()
+        if resume_state_path is not None:                   # core.py:118-126
+            self.load_sampler_state(resume_state_path)
+            t0 = int(self.state.raw("iter") or 0)
+        else:
+            t0 = 0
+            self._initialize_fresh()
+        self.t0 = t0
         self.n_total = int(n_total)
         pbar = None
         if progress:
             from tqdm import tqdm
 
-            pbar = tqdm(desc="Iter")
+            pbar = tqdm(desc="Iter", initial=t0)
         while self._not_termination():
-            self.execute_iteration(export=False)
+            self.execute_iteration(save_every=save_every, t0=t0, export=False)
             if pbar is not None:
                 st = self.state
                 pbar.update(1)
@@ -244,8 +252,96 @@ class SamplerCore:
                                  logZ=st.raw("logz"), acc=st.raw("acceptance"), steps=st.raw("steps"))
         self.state.set_current("logz", float(self._last_posterior_probe[4]))   # core.py:149-150
         self.logz_err = None
+        if save_every is not None:                          # core.py:153-156
+            self.save_sampler_state(self.config.output_dir / f"{self.config.output_label}_final.state")
         if pbar is not None:
             pbar.close()
+
+    # -- checkpoint / resume (core.py:249-315).  The reference pickles the whole sampler with dill and
+    # its load path is broken upstream; this is a plain .npz of the persistent ensemble,
+    # the per-generation scalars and the RNG position, written atomically. ---------------------------
+    STATE_FORMAT = 1
+
+    def save_sampler_state(self, path) -> None:
+        from pathlib import Path
+
+        if self.comm.on:
+            raise NotImplementedError("checkpointing a sharded run is not built yet")
+        path = Path(path)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        ens, st = self.ensemble, self.state
+        n = ens.n_total
+        out = dict(
+            format=np.array(self.STATE_FORMAT), n_dim=np.array(self.config.n_dim),
+            n_particles=np.array(self.config.n_particles),
+            u=ens.u[:n].cpu().numpy(), logl=ens.logl[:n].cpu().numpy(),
+            gen_beta=np.array(ens.gen_beta, dtype=float), gen_logz=np.array(ens.gen_logz, dtype=float),
+            gen_n_local=np.array(ens.gen_n_local, dtype=np.int64),
+            random_state=np.array(-1 if self.config.random_state is None else self.config.random_state),
+            rng_seed=np.array(self.rng.seed, dtype=np.uint64), n_total=np.array(self.n_total),
+        )
+        for key, vals in st._history.items():
+            if key != "blobs":
+                out["hist_" + key] = np.array(vals, dtype=float)
+        for key in ("iter", "calls", "beta", "logz", "steps", "acceptance", "efficiency", "ess", "cv"):
+            v = st.raw(key)
+            out["cur_" + key] = np.array(np.nan if v is None else float(v))
+        for key in ("u", "logl", "assignments"):
+            v = st.raw(key)
+            if v is not None:
+                out["cur_" + key] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        tmp = path.with_suffix(path.suffix + ".temp")
+        with open(tmp, "wb") as f:
+            np.savez(f, **out)
+        tmp.replace(path)
+
+    def load_sampler_state(self, path) -> None:
+        from pathlib import Path
+
+        with np.load(Path(path)) as z:
+            d = {k: z[k] for k in z.files}
+        if int(d["format"]) != self.STATE_FORMAT:
+            raise ValueError(f"unknown state format {int(d['format'])}")
+        if int(d["n_dim"]) != self.config.n_dim:
+            raise ValueError(f"state has n_dim={int(d['n_dim'])}, sampler has n_dim={self.config.n_dim}")
+        ens = PersistentEnsemble(self.config.n_dim, self.device, world=self.comm.world)
+        n = int(d["logl"].shape[0])
+        if n:
+            ens.RESERVE_GENERATIONS = 1                     # size for the history plus room to continue
+            ens._reserve(n + PersistentEnsemble.RESERVE_GENERATIONS * self.n_local)
+            del ens.RESERVE_GENERATIONS
+            ens.u[:n].copy_(torch.as_tensor(d["u"]).to(self.device))
+            ens.logl[:n].copy_(torch.as_tensor(d["logl"]).to(self.device))
+            ens.n_total = n
+            ens.gen_beta = [float(v) for v in d["gen_beta"]]
+            ens.gen_logz = [float(v) for v in d["gen_logz"]]
+            ens.gen_n_local = [int(v) for v in d["gen_n_local"]]
+            ens.gen_n = [int(v) * ens.world for v in d["gen_n_local"]]
+            ens._sync_gens()
+            ens.rebuild_mixture()                           # the cached log-mixture column is derived data
+        self.ensemble = ens
+        st = self.state
+        for key in list(st._history):
+            if key != "blobs" and ("hist_" + key) in d:
+                vals = d["hist_" + key]
+                st._history[key] = [int(v) if key in ("iter", "calls", "steps") else float(v) for v in vals]
+        defaults = {"iter": 0, "calls": 0, "beta": 0.0, "logz": 0.0, "steps": 0, "acceptance": 0.0,
+                    "efficiency": 0.0, "ess": None, "cv": None}                          # core.py:296-309
+        for key, default in defaults.items():
+            v = float(d["cur_" + key]) if ("cur_" + key) in d else float("nan")
+            if np.isnan(v):
+                st.set_current(key, default)
+            else:
+                st.set_current(key, int(v) if key in ("iter", "calls", "steps") else v)
+        for key in ("u", "logl"):
+            if ("cur_" + key) in d:
+                st.set_current(key, torch.as_tensor(d["cur_" + key]).to(self.device))
+        if "cur_assignments" in d:
+            st.set_current("assignments", d["cur_assignments"])
+        st.set_current("x", None)
+        self.n_total = int(d["n_total"])
+        self.rng.seed = int(d["rng_seed"])                  # continue the same counter-based stream
+        self._weights = None
 
     # -- results ----------------------------------------------------------------------------------
     def compute_posterior(self, resample=False, return_blobs=False, trim_importance_weights=True,

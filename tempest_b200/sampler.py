@@ -91,11 +91,11 @@ class Sampler:
     def results(self):
         return self.state.compute_results()
 
-    def save_state(self, path):
-        raise NotImplementedError("checkpointing is outside the hot path (SURVEY 8f-4)")
+    def save_state(self, path):                          # sampler.py:278-287
+        self._core.save_sampler_state(Path(path))
 
-    def load_state(self, path):
-        raise NotImplementedError("checkpointing is outside the hot path (SURVEY 8f-4)")
+    def load_state(self, path):                          # sampler.py:289-298
+        self._core.load_sampler_state(Path(path))
 
     # -- read-only properties (sampler.py:313-406) ---------------------------------------------
     n_dim = property(lambda self: self._core.config.n_dim)
