@@ -257,7 +257,8 @@ int tb_transform(const double* u, int64_t n, const tb_mcmc_params* p, double* x,
 size_t tb_mcmc_workspace_bytes(int64_t n, int32_t n_modes);
 size_t tb_mcmc_ctrl_doubles(int32_t n_modes);
 /* reset the control block (sigma_c init, mcmc.py:222-223/298-299), count walkers per mode and
- * cache q_k = (u_k-mu)^T Sigma^-1 (u_k-mu) of the starting state (tpCN) */
+ * cache q_k = (u_k-mu)^T Sigma^-1 (u_k-mu) of the starting state (tpCN).  qcur holds 2n doubles:
+ * q_k in [0,n) and the Student-t term -(D+nu)/2 log(1+q_k/nu) of the current state in [n,2n). */
 int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, const double* u,
                   double* qcur, void* workspace, double* ctrl, tb_stream_t stream);
 /* enqueue `count` Metropolis steps (each exits immediately once the stop rule has fired) */

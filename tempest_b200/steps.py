@@ -824,7 +824,7 @@ class Mutator:
             raise IndexError(f"walker assigned to cluster {int(assign.max().item())} but only {K} modes were fitted")
         ctrl = k.ws.f64("mcmc_ctrl", int(lib.tb_mcmc_ctrl_doubles(K)))
         ws = k.ws.bytes("mcmc_ws", lib.tb_mcmc_workspace_bytes(n, K))
-        qcur = k.ws.f64("mcmc_q", n)
+        qcur = k.ws.f64("mcmc_q", 2 * n)                 # q_k and the cached Student-t term of the current state
         _lib.check(lib.tb_mcmc_begin(n, C.byref(params), ptr(assign), ptr(u), ptr(qcur), ptr(ws), ptr(ctrl), sp),
                    "tb_mcmc_begin")
         tape = core.rng.mcmc_tape(n, d)

@@ -12,6 +12,20 @@ import tempest_b200 as tp  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 d = 10
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if local != 0:
+        sys.stdout = open(os.devnull, "w")
+for _warm in range(int(os.environ.get("PROFILE_WARM_RUNS", "0"))):     # untimed: module loading, allocations
+    _s = tp.Sampler(tp.UniformPrior(-10.0, 10.0, d), tp.Rosenbrock(d), d, n_particles=n, vectorize=True,
+                    clustering=False, random_state=20261018)
+    _s.run(progress=False)
+    del _s
 s = tp.Sampler(tp.UniformPrior(-10.0, 10.0, d), tp.Rosenbrock(d), d, n_particles=n, vectorize=True,
                clustering=False, random_state=20261018)
 core = s._core
@@ -44,4 +58,8 @@ print("stage sums (iterations 6..T, ms):", {k_: round(v, 1) for k_, v in sorted(
 print(f"T={len(rows)} total {total:.3f} s  -> {len(rows) / total:.2f} it/s, calls {core.state.raw('calls')}, "
       f"{core.state.raw('calls') / total:.3e} evals/s")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "profile_run.json"), "w"))
+if local == 0:
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", f"profile_run_g{world}.json"), "w"))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
