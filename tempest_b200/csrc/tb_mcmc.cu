@@ -325,7 +325,9 @@ int tb_set_mcmc_generic(int32_t on) { tb_force_generic_mcmc = on ? 1 : 0; return
 
 size_t tb_mcmc_workspace_bytes(int64_t n, int32_t n_modes) {
   const int64_t grid = (n + kMcmcBlock - 1) / kMcmcBlock;
-  return 256 + sizeof(double) * (size_t)grid * (n_modes + 3);
+  const size_t flat = 256 + sizeof(double) * (size_t)grid * (n_modes + 3);
+  const size_t tree = 256 + fold_workspace_bytes((int)((n + kFastBlock - 1) / kFastBlock), n_modes + 3);
+  return flat > tree ? flat : tree;
 }
 size_t tb_mcmc_ctrl_doubles(int32_t n_modes) { return C_BASE + 4 * (size_t)n_modes + 3; }
 
@@ -370,7 +372,8 @@ int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, con
       !ctrl)
     return TB_ERR_ARG;
   cudaStream_t st = as_stream(stream);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, 16, st);
+  // global ticket + the group tickets of the fast kernel's hierarchical fold
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 16 + fold_ticket_bytes((int)((n + kFastBlock - 1) / kFastBlock)), st);
   if (e != cudaSuccess) return (int)e;
   mcmc_init_ctrl_kernel<<<1, 256, 0, st>>>(*p, ctrl);
   const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);

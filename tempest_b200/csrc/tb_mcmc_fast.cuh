@@ -31,7 +31,7 @@ __device__ __forceinline__ void bm_pair32(uint32_t a, uint32_t b, double& z0, do
 // resident CTAs per SM the register allocation is held to (measured at D = 10: 6 CTAs / 80 registers
 // beat 5 CTAs / 96 registers by ~3 %)
 template <int D>
-constexpr int mcmc_min_ctas() { return D <= 10 ? 6 : (D <= 12 ? 4 : 3); }
+constexpr int mcmc_min_ctas() { return (D <= 10 ? 6 : (D <= 12 ? 4 : 3)) * (128 / kFastBlock); }
 
 // Single-mode production runs (K = 1, the clustering=False headline path) read the mode statistics and the
 // prior box from constant memory: the operands fold into the DFMAs, so the ~3 D^2/2 shared-memory loads per
@@ -41,11 +41,11 @@ constexpr int kConstDoubles = 16 + 2 * 256 + 32 + 1;
 static __constant__ double c_mode[kConstDoubles];
 
 template <int D, bool TPCN, bool TAPE, bool KONE>
-__global__ void __launch_bounds__(kMcmcBlock, mcmc_min_ctas<D>())
+__global__ void __launch_bounds__(kFastBlock, mcmc_min_ctas<D>())
 mcmc_step_fast(StepArgs a) {
   if (a.ctrl[C_DONE] != 0.0) return;
   constexpr int CM_CHOL = D, CM_INV = D + D * D, CM_PRIOR = D + 2 * D * D, CM_DOF = D + 2 * D * D + 2 * D;
-  constexpr int B = kMcmcBlock;
+  constexpr int B = kFastBlock, NW = B / 32;         // one-warp CTAs by default: no CTA-wide barrier anywhere
   constexpr int NCALL = (D + 3) / 4;                 // Philox blocks per attempt (4 normals each)
   extern __shared__ double sm[];
   __shared__ double s_x[D][B];                       // proposal centre, later the winning proposal
@@ -61,8 +61,8 @@ mcmc_step_fast(StepArgs a) {
   double* s_inv = s_chol + K * D * D;                // symmetric form: diagonal as is, off-diagonals doubled (upper)
   double* s_dof = s_inv + K * D * D;
   double* s_sig = s_dof + K;
-  double* s_part = s_sig + K;                        // [4][K] per-warp alpha sums
-  double* s_prior = s_part + 4 * K;                  // [2*D] lo, scale
+  double* s_part = s_sig + K;                        // [NW][K] per-warp alpha sums
+  double* s_prior = s_part + NW * K;                 // [2*D] lo, scale
   if (!KONE) {
     for (int e = threadIdx.x; e < K * D; e += B) s_mean[e] = __ldg(a.p.mode_mean + e);
     for (int e = threadIdx.x; e < K * D * D; e += B) {
@@ -73,7 +73,7 @@ mcmc_step_fast(StepArgs a) {
     }
     for (int e = threadIdx.x; e < K; e += B) { s_dof[e] = __ldg(a.p.mode_dof + e); s_sig[e] = a.ctrl[C_BASE + e]; }
     for (int e = threadIdx.x; e < 2 * D; e += B) s_prior[e] = __ldg(a.p.prior_params + e);
-    __syncthreads();
+    if (NW > 1) __syncthreads(); else __syncwarp();
   }
   // quadratic form (u - mu)^T Sigma^-1 (u - mu) of mode `cm` from centred coordinates
   auto quad = [&](const double (&dv)[D], int cm) -> double {
@@ -299,28 +299,36 @@ mcmc_step_fast(StepArgs a) {
     const double v = warp_sum((valid && c == m) ? alpha : 0.0);
     if (lane == 0) s_part[wid * K + m] = v;
   }
-  __shared__ double s_tot[4][3];
+  __shared__ double s_tot[NW][3];
+  __shared__ double s_fold[kMaxModes + 3];
   {
     const double na = warp_sum((double)accepted), npr = warp_sum((double)nprop), ne = warp_max((double)err);
     if (lane == 0) { s_tot[wid][0] = na; s_tot[wid][1] = npr; s_tot[wid][2] = ne; }
   }
-  __syncthreads();
+  if (NW > 1) __syncthreads(); else __syncwarp();
   const int W = K + 3;
-  double* part = a.ws->partial + (size_t)blockIdx.x * W;
-  for (int m = t; m < K; m += B) part[m] = ((s_part[m] + s_part[K + m]) + s_part[2 * K + m]) + s_part[3 * K + m];
-  if (t == 0) {
-    part[K] = ((s_tot[0][0] + s_tot[1][0]) + s_tot[2][0]) + s_tot[3][0];
-    part[K + 1] = ((s_tot[0][1] + s_tot[1][1]) + s_tot[2][1]) + s_tot[3][1];
-    part[K + 2] = fmax(fmax(s_tot[0][2], s_tot[1][2]), fmax(s_tot[2][2], s_tot[3][2]));
+  double* part = fold_cta_partials(a.ws, gridDim.x, W) + (size_t)blockIdx.x * W;
+  for (int m = t; m < K; m += B) {
+    double v = s_part[m];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) v += s_part[w * K + m];
+    part[m] = v;
   }
-  if (last_block_arrives(&a.ws->ticket)) finish_step(a, K, gridDim.x);
+  if (t == 0) {
+    double na = s_tot[0][0], npr = s_tot[0][1], ne = s_tot[0][2];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) { na += s_tot[w][0]; npr += s_tot[w][1]; ne = fmax(ne, s_tot[w][2]); }
+    part[K] = na; part[K + 1] = npr; part[K + 2] = ne;
+  }
+  if (NW > 1) __syncthreads();
+  if (wid == 0) arrive_and_fold(a, K, s_fold);
 }
 
 
 template <int D, bool TPCN, bool TAPE, bool KONE>
 int launch_fast_variant(const StepArgs& a, int count, cudaStream_t st) {
   const int K = a.p.n_modes;
-  const size_t smem = sizeof(double) * ((size_t)K * D + 2 * (size_t)K * D * D + 2 * K + 4 * K + 2 * D);
+  const size_t smem = sizeof(double) * ((size_t)K * D + 2 * (size_t)K * D * D + 2 * K + (kFastBlock / 32) * K + 2 * D);
   if (smem > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mcmc_step_fast<D, TPCN, TAPE, KONE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -336,8 +344,8 @@ int launch_fast_variant(const StepArgs& a, int count, cudaStream_t st) {
                                             kd, st);
     if (e != cudaSuccess) return (int)e;
   }
-  const int grid = (int)((a.n + kMcmcBlock - 1) / kMcmcBlock);
-  for (int s = 0; s < count; ++s) mcmc_step_fast<D, TPCN, TAPE, KONE><<<grid, kMcmcBlock, smem, st>>>(a);
+  const int grid = (int)((a.n + kFastBlock - 1) / kFastBlock);
+  for (int s = 0; s < count; ++s) mcmc_step_fast<D, TPCN, TAPE, KONE><<<grid, kFastBlock, smem, st>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? TB_OK : (int)e;
 }

@@ -7,7 +7,12 @@
 
 namespace tb {
 
-constexpr int kMcmcBlock = 128;
+constexpr int kMcmcBlock = 128;      // walkers per CTA of the runtime-dimension kernels
+#ifndef TB_FAST_BLOCK
+#define TB_FAST_BLOCK 32
+#endif
+constexpr int kFastBlock = TB_FAST_BLOCK;   // walkers per CTA of the compile-time-dimension kernel
+constexpr int kFoldGroup = 32;              // CTAs whose partials one group leader folds
 constexpr int kMaxModes = 64;
 constexpr int kMaxAttempts = 100000;
 
@@ -54,16 +59,85 @@ __device__ __forceinline__ double bc_apply(double v, int kind) {
 
 __device__ inline void apply_step_update(const tb_mcmc_params& p, double* ctrl, const double* tot, int K);
 
+// Workspace of the fast kernel (after the 16-byte header with the global ticket): one ticket per group
+// of kFoldGroup CTAs, the group partials [ngroups][W], then the CTA partials [grid][W].
+__host__ __device__ inline int fold_groups(int grid) { return (grid + kFoldGroup - 1) / kFoldGroup; }
+__host__ __device__ inline size_t fold_ticket_bytes(int grid) { return ((size_t)fold_groups(grid) * 4 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t fold_workspace_bytes(int grid, int W) {
+  return 16 + fold_ticket_bytes(grid) + sizeof(double) * (size_t)W * ((size_t)fold_groups(grid) + (size_t)grid);
+}
+__device__ inline unsigned int* fold_tickets(McmcWs* ws) { return reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + 16); }
+__device__ inline double* fold_group_partials(McmcWs* ws, int grid) {
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 16 + fold_ticket_bytes(grid));
+}
+__device__ inline double* fold_cta_partials(McmcWs* ws, int grid, int W) {
+  return fold_group_partials(ws, grid) + (size_t)fold_groups(grid) * W;
+}
+
+__device__ inline void finish_tail(const StepArgs& a, int K, double* tot, int nth);
+
 // fold the per-CTA partials, adapt sigma and evaluate the stop rule (mcmc.py:180-194, 104-135)
 __device__ inline void finish_step(const StepArgs& a, int K, int nparts) {
   __shared__ double tot[kMaxModes + 3];
+  __shared__ double red[40];
   const int W = K + 3;
-  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+  // every thread sums a strided share of the rows, then a fixed-order CTA sum per column (a single
+  // thread walking all rows costs ~30 ns per dependent L2 load: 0.25 ms at 8192 CTAs)
+  for (int c = 0; c < W; ++c) {
     double t = 0.0;
-    for (int b = 0; b < nparts; ++b) t += __ldcg(a.ws->partial + (size_t)b * W + c);
-    tot[c] = t;
+    for (int b = threadIdx.x; b < nparts; b += blockDim.x) t += __ldcg(a.ws->partial + (size_t)b * W + c);
+    t = block_sum(t, red);
+    if (threadIdx.x == 0) tot[c] = t;
   }
   __syncthreads();
+  finish_tail(a, K, tot, blockDim.x);
+}
+
+// Hierarchical, order-fixed fold for the fast kernel, executed by warp 0 of every CTA after the CTA's
+// partial row is in memory: the last CTA of each group of kFoldGroup folds the group, the last group
+// leader folds the groups and applies the update.  No CTA ever waits for another.
+__device__ inline void arrive_and_fold(const StepArgs& a, int K, double* tot /* shared, >= K+3 */) {
+  const int W = K + 3, grid = gridDim.x, lane = threadIdx.x & 31;
+  const int ngroups = fold_groups(grid);
+  unsigned int* gticket = fold_tickets(a.ws);
+  double* gpart = fold_group_partials(a.ws, grid);
+  const double* cpart = fold_cta_partials(a.ws, grid, W);
+  const int g = blockIdx.x / kFoldGroup;
+  const int gsize = min(kFoldGroup, grid - g * kFoldGroup);
+  __threadfence();
+  __syncwarp();
+  unsigned int tk = 0;
+  if (lane == 0) tk = atomicAdd(&gticket[g], 1u);
+  tk = __shfl_sync(0xffffffffu, tk, 0);
+  if (tk != (unsigned)(gsize - 1)) return;
+  if (lane == 0) gticket[g] = 0u;
+  __threadfence();
+  for (int c = 0; c < W; ++c) {
+    double v = (lane < gsize) ? __ldcg(cpart + ((size_t)g * kFoldGroup + lane) * W + c) : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) gpart[(size_t)g * W + c] = v;
+  }
+  __threadfence();
+  __syncwarp();
+  unsigned int t2 = 0;
+  if (lane == 0) t2 = atomicAdd(&a.ws->ticket, 1u);
+  t2 = __shfl_sync(0xffffffffu, t2, 0);
+  if (t2 != (unsigned)(ngroups - 1)) return;
+  if (lane == 0) a.ws->ticket = 0u;
+  __threadfence();
+  for (int c = 0; c < W; ++c) {
+    double v = 0.0;
+    for (int q = lane; q < ngroups; q += 32) v += __ldcg(gpart + (size_t)q * W + c);
+    v = warp_sum(v);
+    if (lane == 0) tot[c] = v;
+  }
+  __syncwarp();
+  finish_tail(a, K, tot, 32);
+}
+
+// `nth` = number of threads (threadIdx.x < nth) executing this call
+__device__ inline void finish_tail(const StepArgs& a, int K, double* tot, int nth) {
+  const int W = K + 3;
   if (a.x.world > 1) {
     // fused collective: exchange this rank's (sum alpha per mode, accepted, proposals, error) with every
     // peer over NVLink and fold them in rank order, then adapt sigma / evaluate the stop rule right here
@@ -82,7 +156,7 @@ __device__ inline void finish_step(const StepArgs& a, int K, int nparts) {
   }
   if (a.p.defer_update) {
     // sharded run: leave this rank's totals for the host to all-reduce; tb_mcmc_update applies them
-    for (int c = threadIdx.x; c < W; c += blockDim.x) a.ctrl[C_BASE + 3 * K + c] = tot[c];
+    for (int c = threadIdx.x; c < W; c += nth) a.ctrl[C_BASE + 3 * K + c] = tot[c];
     return;
   }
   if (threadIdx.x == 0) apply_step_update(a.p, a.ctrl, tot, K);
