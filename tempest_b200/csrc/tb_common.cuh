@@ -113,6 +113,21 @@ __device__ __forceinline__ bool last_block_arrives(unsigned int* ticket) {
   return is_last;
 }
 
+// Order-fixed sum of column `col` over `rows` partial rows of width `stride`, with eight independent
+// accumulators so that eight L2 loads are in flight (a single running sum serialises on the ~0.6 us
+// round trip per unrolled group and turns last-CTA epilogues into 30-200 us tails).
+__device__ __forceinline__ double fold_column(const double* __restrict__ partial, int rows, size_t stride, int col) {
+  double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  int b = 0;
+  for (; b + 8 <= rows; b += 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += __ldcg(partial + (size_t)(b + q) * stride + col);
+  }
+  double tail = 0.0;
+  for (; b < rows; ++b) tail += __ldcg(partial + (size_t)b * stride + col);
+  return (((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]))) + tail;
+}
+
 // Streaming (max, S1, S2) accumulator of w = exp(a - max a) and w^2 with online rescaling.
 struct Ess3 {
   double m, s1, s2;

@@ -546,10 +546,24 @@ mom_mean_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, 
   const int col = threadIdx.x % d, r0 = threadIdx.x / d;
   double acc = 0.0;
   if (threadIdx.x < act) {
-    for (int64_t j = (int64_t)blockIdx.x * rpb + r0; j < n; j += (int64_t)gridDim.x * rpb) {
-      const int64_t r = rows ? __ldg(rows + j) : j;
-      acc += wt_load(w, j) * __ldg(u + r * d + col);
+    // four independent accumulators: four rows of loads in flight per thread
+    const int64_t step = (int64_t)gridDim.x * rpb;
+    int64_t j = (int64_t)blockIdx.x * rpb + r0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (; j + 3 * step < n; j += 4 * step) {
+      const int64_t j1 = j + step, j2 = j + 2 * step, j3 = j + 3 * step;
+      const int64_t q0 = rows ? __ldg(rows + j) : j, q1 = rows ? __ldg(rows + j1) : j1;
+      const int64_t q2 = rows ? __ldg(rows + j2) : j2, q3 = rows ? __ldg(rows + j3) : j3;
+      a0 += wt_load(w, j) * __ldg(u + q0 * d + col);
+      a1 += wt_load(w, j1) * __ldg(u + q1 * d + col);
+      a2 += wt_load(w, j2) * __ldg(u + q2 * d + col);
+      a3 += wt_load(w, j3) * __ldg(u + q3 * d + col);
     }
+    for (; j < n; j += step) {
+      const int64_t r = rows ? __ldg(rows + j) : j;
+      a0 += wt_load(w, j) * __ldg(u + r * d + col);
+    }
+    acc = (a0 + a1) + (a2 + a3);
   }
   red[threadIdx.x] = (threadIdx.x < act) ? acc : 0.0;
   __syncthreads();
@@ -561,8 +575,7 @@ mom_mean_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, 
   }
   if (last_block_arrives(&ws->ticket)) {
     if (threadIdx.x < d) {
-      double t = 0.0;
-      for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(ws->partial + (size_t)b * d + threadIdx.x);
+      const double t = fold_column(ws->partial, (int)gridDim.x, (size_t)d, threadIdx.x);
       mean[threadIdx.x] = t * inv_norm;
     }
   }
@@ -651,8 +664,7 @@ mom_cov_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, c
   }
   if (last_block_arrives(&ws->ticket)) {
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
-      double t = 0.0;
-      for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(ws->partial + (size_t)b * P + p);
+      const double t = fold_column(ws->partial, (int)gridDim.x, (size_t)P, p);
       const int j = pj[p], k = pk[p];
       cov[j * d + k] = t;
       cov[k * d + j] = t;
@@ -753,13 +765,61 @@ mom_cov_small_kernel(const double* __restrict__ u, const int64_t* __restrict__ r
   }
   if (last_block_arrives(&ws->ticket)) {
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
-      double t = 0.0;
-      for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(ws->partial + (size_t)b * P + p);
+      const double t = fold_column(ws->partial, (int)gridDim.x, (size_t)P, p);
       int a = 0, rem = p;
       while (rem >= D - a) { rem -= D - a; ++a; }
       const int bcol = a + rem;
       cov[a * D + bcol] = t;
       cov[bcol * D + a] = t;
+    }
+  }
+}
+
+// column sums, same one-row-per-thread streaming pattern (the column-per-thread kernel above peaks at
+// ~2.7 TB/s; this one reads rows like mom_cov_small and runs at its ~4.6 TB/s)
+template <int D, typename WT>
+__global__ void __launch_bounds__(kSmallBlock)
+mom_mean_small_kernel(const double* __restrict__ u, const int64_t* __restrict__ rows, const WT* __restrict__ w,
+                      int64_t n, double inv_norm, MomWs* ws, double* __restrict__ mean) {
+  __shared__ double red[kSmallBlock / 32][D];
+  double acc[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) acc[c] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const int64_t r = rows ? __ldg(rows + j) : j;
+    const double wj = wt_load(w, j);
+    const double* row = u + r * D;
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] += wj * __ldg(row + c);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const double v = warp_sum(acc[c]);
+    if (lane == 0) red[wid][c] = v;
+  }
+  __syncthreads();
+  double* part = ws->partial + (size_t)blockIdx.x * D;
+  if (threadIdx.x < D) {
+    double t = 0.0;
+    for (int q = 0; q < kSmallBlock / 32; ++q) t += red[q][threadIdx.x];
+    part[threadIdx.x] = t;
+  }
+  if (last_block_arrives(&ws->ticket)) {
+    // D columns x 8 strided shares, then a fixed-order sum of the shares
+    __shared__ double share[8][D];
+    const int c = threadIdx.x % D, q = threadIdx.x / D;
+    if (q < 8) {
+      double t = 0.0;
+      for (int b = q; b < (int)gridDim.x; b += 8) t += __ldcg(ws->partial + (size_t)b * D + c);
+      share[q][c] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {
+      double t = 0.0;
+      for (int q2 = 0; q2 < 8; ++q2) t += share[q2][threadIdx.x];
+      mean[threadIdx.x] = t * inv_norm;
     }
   }
 }
@@ -823,6 +883,18 @@ bool launch_cov_small(int d, int grid, const double* u, const int64_t* rows, con
   }
 }
 
+template <typename WT>
+bool launch_mean_small(int d, int grid, const double* u, const int64_t* rows, const WT* w, int64_t n, double inv_norm,
+                       MomWs* ws, double* mean, cudaStream_t st) {
+  switch (d) {
+#define TB_CASE(DD) case DD: mom_mean_small_kernel<DD, WT><<<grid, kSmallBlock, 0, st>>>(u, rows, w, n, inv_norm, ws, mean); return true;
+    TB_CASE(1) TB_CASE(2) TB_CASE(3) TB_CASE(4) TB_CASE(5) TB_CASE(6) TB_CASE(7) TB_CASE(8) TB_CASE(9) TB_CASE(10)
+    TB_CASE(12) TB_CASE(16)
+#undef TB_CASE
+    default: return false;
+  }
+}
+
 inline bool launch_mahal_small(int d, int grid, const double* u, const double* w, int64_t n, const double* mean,
                                const double* inv, ReduceWs* ws, double* out, cudaStream_t st) {
   switch (d) {
@@ -846,7 +918,8 @@ int launch_moments(const double* u, const int64_t* rows, const WT* w, int64_t n,
   if (n <= 0 || d <= 0 || d > kMomMaxD || !u || !w || !workspace || !mean) return TB_ERR_ARG;
   MomWs* ws = (MomWs*)workspace;
   const int grid = mom_grid(n, d);
-  if (do_mean) mom_mean_kernel<WT><<<grid, kBlock, 0, st>>>(u, rows, w, n, d, inv_norm, ws, mean);
+  if (do_mean && !launch_mean_small<WT>(d, small_grid(n), u, rows, w, n, inv_norm, ws, mean, st))
+    mom_mean_kernel<WT><<<grid, kBlock, 0, st>>>(u, rows, w, n, d, inv_norm, ws, mean);
   if (cov && launch_cov_small<WT>(d, small_grid(n), u, rows, w, n, mean, ws, cov, st)) {
     // register-resident fast path (d <= 10)
   } else if (cov) {
