@@ -44,7 +44,40 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
 
+    def _nvml_loop(self) -> bool:
+        """In-process NVML sampling (same counters as nvidia-smi, without forking a process that takes the
+        driver lock every 200 ms inside the timed region)."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                     else nv.nvmlClocksThrottleReasonHwSlowdown),
+                    ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                    getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0))),
+                    ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                    getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0))),
+                    ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0)))]
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        while not self._halt.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = get_reasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if (mask & b) else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self._halt.wait(0.05)
+        return True
+
     def run(self):
+        if self._nvml_loop():
+            return
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -180,7 +213,8 @@ def main():
     ws_ = tp.Sampler(tp.UniformPrior(-10.0, 10.0, N_DIM), tp.Rosenbrock(N_DIM), N_DIM, n_particles=n_particles,
                      vectorize=True, clustering=False, random_state=1)
     ws_.run(n_total=4096, progress=False)      # same shape as the timed workload: the caching allocator keeps its blocks
-    del ws_
+    _ = ws_.posterior()                        # ... and the page-locked staging blocks of the posterior read-back
+    del ws_, _
     barrier()
 
     # ---- device-timed region: K PS iterations after W warm-up iterations ---------------------------
@@ -205,6 +239,10 @@ def main():
     for _ in range(args.warmup):
         one_iteration()
     barrier()
+    import gc
+
+    gc.collect()
+    gc.disable()                               # no collector pauses inside the timed regions
     clocks = ClockSampler(local)
     clocks.start()
     calls0 = core.state.raw("calls")
@@ -213,12 +251,18 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     calls_acc = 0
+    trace = os.environ.get("BENCH_TRACE")
+    marks = []
     for _ in range(args.steps):
         before = core.state.raw("calls")
         one_iteration()
         after = core.state.raw("calls")
         calls_acc += after - (before if after >= before else 0)
+        if trace:
+            marks.append(round(time.perf_counter(), 4))
     ev1.record()
+    if trace:
+        print("iteration host marks (s):", [round(b - a, 4) for a, b in zip(marks[:-1], marks[1:])], file=sys.stderr)
     launches = _lib.launch_count - launches0
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -236,10 +280,13 @@ def main():
     t0 = time.perf_counter()
     s2 = new_sampler()
     s2.run(n_total=4096, progress=False)
+    t_run = time.perf_counter() - t0
     logz, _ = s2.evidence()
     x, w, l = s2.posterior()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if trace:
+        print(f"e2e: run {t_run:.3f} s, posterior {dt - t_run:.3f} s", file=sys.stderr)
     T2 = s2.state.get_history_length()
     d2h = (x.nbytes + w.nbytes + l.nbytes) / T2 + 16 * 8 * 12 + 3 * 2048 * 8
     h2d = 3 * T2 * 8 + 64
@@ -249,6 +296,7 @@ def main():
            "note": "Sampler(...).run(4096) + evidence() + posterior() to host numpy; inputs are the problem "
                    "definition (parameters), outputs the weighted posterior sample"}
     del x, w, l
+    gc.enable()
 
     # ---- roofline of the HBM-bound hot kernel, measured live on the FULL persistent ensemble of that run:
     #      the ESS probe streams logl[] and C[] once = 16 algorithmic bytes per stored particle ---------------

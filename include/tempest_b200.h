@@ -97,6 +97,11 @@ int tb_cdf_sequential(const double* p, int64_t n, double* cdf, tb_stream_t strea
 /* multinomial: idx_k = #{ j : cdf_j / cdf_{n-1} <= U_k }   (searchsorted side='right') */
 int tb_search_right(const double* cdf, int64_t n, const double* draws, int64_t m,
                     int64_t* idx, tb_stream_t stream);
+/* the same indices for many draws: a guide table over 2^bits uniform grid points brackets every draw so
+ * the search needs ~2-3 probes; guide: tb_search_guide_bytes(bits) bytes of scratch */
+size_t tb_search_guide_bytes(int32_t bits);
+int tb_search_right_guided(const double* cdf, int64_t n, const double* draws, int64_t m, void* guide,
+                           int32_t bits, int64_t* idx, tb_stream_t stream);
 /* systematic: pos_k = (u0 + k)/m ; idx_k = first j with cdf_j >= pos_k ; *overflow is set
  * to 1 if some pos_k exceeds cdf_{n-1} (the reference raises IndexError there). */
 int tb_systematic(const double* cdf, int64_t n, double u0, int64_t m, int64_t* idx,

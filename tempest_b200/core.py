@@ -375,8 +375,20 @@ class SamplerCore:
             x, w, logl = (self.comm.allgather_rows(t.contiguous()) for t in (x, w, logl))
             if logw is not None:
                 logw = self.comm.allgather_rows(torch.as_tensor(logw).to(self.device)).cpu().numpy()
-        out = (x.cpu().numpy(), w.cpu().numpy(), logl.cpu().numpy())
+        out = tuple(self._to_host(t) for t in (x, w, logl))
         return out + (logw,) if return_logw else out
+
+    @staticmethod
+    def _to_host(t: torch.Tensor) -> np.ndarray:
+        """Device -> host through page-locked memory (the weighted posterior of a 2^20-particle run is
+        ~600 MB; a pageable ``.cpu()`` moves it at ~2 GB/s).  The numpy array owns the pinned block; torch's
+        host allocator recycles it once the array is released."""
+        if t.numel() < (1 << 16):
+            return t.cpu().numpy()
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
 
     def compute_evidence(self):
         return self.state.raw("logz"), self.logz_err

@@ -16,6 +16,7 @@ PyTorch is used for allocation, streams and host copies only.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import math
 from typing import Dict, List, Optional
 
@@ -136,7 +137,7 @@ class DeviceState:
 
     def __init__(self, n_dim: int, core=None):
         self.n_dim = n_dim
-        self._core = core
+        self._core = weakref.proxy(core) if core is not None else None
         self._current: Dict[str, object] = {k: None for k in CURRENT_STATE_KEYS}
         self._history: Dict[str, list] = {k: [] for k in HISTORY_STATE_KEYS if k not in ("u", "x", "logl", "blobs")}
         self._history["blobs"] = []

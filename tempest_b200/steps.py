@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -213,8 +214,15 @@ class Kernels:
         return out
 
     def search_right(self, cdf: torch.Tensor, n: int, draws: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-        _lib.check(self.lib.tb_search_right(ptr(cdf), n, ptr(draws), draws.numel(), ptr(out), stream_ptr()),
-                   "tb_search_right")
+        m = int(draws.numel())
+        if m >= 1 << 16 and n >= 1 << 12:
+            # many draws: bracket each one with a guide table (identical indices, ~3 probes instead of log2 n)
+            bits = max(10, min(20, (m // 8).bit_length() - 1))
+            guide = self.ws.bytes("search_guide", self.lib.tb_search_guide_bytes(bits))
+            _lib.check(self.lib.tb_search_right_guided(ptr(cdf), n, ptr(draws), m, ptr(guide), bits, ptr(out),
+                                                       stream_ptr()), "tb_search_right_guided")
+            return out
+        _lib.check(self.lib.tb_search_right(ptr(cdf), n, ptr(draws), m, ptr(out), stream_ptr()), "tb_search_right")
         return out
 
     def systematic(self, cdf: torch.Tensor, n: int, u0: float, m: int, out: torch.Tensor) -> torch.Tensor:
@@ -414,7 +422,7 @@ class Reweighter:
     """steps/reweight.py:341-495."""
 
     def __init__(self, core):
-        self.core = core
+        self.core = weakref.proxy(core)      # the core owns the steps; no reference cycle, so memory frees on del
         cfg = core.config
         self.n_particles = cfg.n_particles
         self.ess_ratio = cfg.ess_ratio
@@ -560,7 +568,7 @@ class Trainer:
     """steps/train.py:65-127 + modes.py:131-288 + student.py:6-116."""
 
     def __init__(self, core):
-        self.core = core
+        self.core = weakref.proxy(core)      # the core owns the steps; no reference cycle, so memory frees on del
 
     def run(self, weights: Optional[torch.Tensor]) -> ModeStats:
         core = self.core
@@ -697,7 +705,7 @@ class Resampler:
     """steps/resample.py:52-99."""
 
     def __init__(self, core):
-        self.core = core
+        self.core = weakref.proxy(core)      # the core owns the steps; no reference cycle, so memory frees on del
 
     def run(self, weights: Optional[torch.Tensor]) -> None:
         core = self.core
@@ -774,7 +782,7 @@ class Mutator:
                     return h, launched
 
     def __init__(self, core):
-        self.core = core
+        self.core = weakref.proxy(core)      # the core owns the steps; no reference cycle, so memory frees on del
 
     def run(self, mode_stats: ModeStats) -> None:
         core = self.core

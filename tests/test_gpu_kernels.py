@@ -475,3 +475,32 @@ def test_split_by_label_keeps_order(env):
         c1 = int(cnt.item())
         np.testing.assert_array_equal(one[:c1].cpu().numpy(), members[labels != 0])
         np.testing.assert_array_equal(zero[:n - c1].cpu().numpy(), members[labels == 0])
+
+
+def test_guided_search_equals_plain_search(env):
+    """tb_search_right_guided must return exactly the indices of the full binary search, including draws
+    that sit on guide grid points, on cdf values, and in flat (zero-weight) stretches."""
+    rng = np.random.default_rng(12)
+    n, m = 200_000, 300_000
+    p = np.exp(-0.5 * rng.chisquare(4, n) * 9.0)
+    p[rng.integers(0, n, n // 10)] = 0.0
+    p[1000:30000] = 0.0
+    p /= p.sum()
+    dp = dev_arr(env, p)
+    cdf = env.k.cdf(dp, n, "g_cdf")
+    c = cdf.cpu().numpy()
+    u = rng.random(m)
+    u[:4096] = np.arange(4096) / 4096.0                       # guide grid points of every table size
+    u[4096:8192] = np.minimum(c[rng.integers(0, n, 4096)] / c[-1], np.nextafter(1.0, 0.0))   # exactly on cdf values
+    u[8192] = np.nextafter(1.0, 0.0)
+    du = dev_arr(env, u)
+    plain = torch.empty(m, dtype=torch.int64, device=env.dev)
+    assert env.lib.tb_search_right(env.ptr(cdf), n, env.ptr(du), m, env.ptr(plain), env.sp()) == 0
+    ref = (c / c[-1]).searchsorted(u, side="right")
+    np.testing.assert_array_equal(plain.cpu().numpy(), ref)
+    for bits in (4, 10, 15, 20):
+        guide = torch.zeros(env.lib.tb_search_guide_bytes(bits), dtype=torch.uint8, device=env.dev)
+        out = torch.empty(m, dtype=torch.int64, device=env.dev)
+        assert env.lib.tb_search_right_guided(env.ptr(cdf), n, env.ptr(du), m, env.ptr(guide), bits, env.ptr(out),
+                                              env.sp()) == 0
+        np.testing.assert_array_equal(out.cpu().numpy(), ref, err_msg=f"bits={bits}")
