@@ -152,6 +152,9 @@ size_t tb_reduce_workspace_bytes(void);
 int tb_normalize_inplace(double* w, int64_t n, void* workspace, double* stats3, tb_stream_t stream);
 int tb_binade_hist(const double* w, int64_t n, uint64_t* count2048, double* s1_2048,
                    double* s2_2048, tb_stream_t stream);
+/* the same three sums over the 2048 linear sub-bins (top 11 mantissa bits) of one binade */
+int tb_subbin_hist(const double* w, int64_t n, int32_t binade, uint64_t* count2048, double* s1_2048,
+                   double* s2_2048, tb_stream_t stream);
 int tb_masked_sums(const double* w, int64_t n, double thr, void* workspace, double* out3,
                    tb_stream_t stream);
 size_t tb_compact_workspace_bytes(int64_t n);
@@ -229,7 +232,9 @@ typedef struct tb_mcmc_params {
   int32_t n_dim, n_modes, sampler, rng_mode;
   int32_t like_id, prior_id;
   int32_t n_steps, n_max;          /* per-dimension base / max step counts (config.py:80-84) */
-  int32_t defer_update, reserved;  /* 1: sharded run, leave per-step totals for an all-reduce + tb_mcmc_update */
+  int32_t defer_update, reserved;  /* defer_update 1: sharded run, leave per-step totals for an all-reduce +
+                                    * tb_mcmc_update.  reserved != 0: mode statistics / prior parameters are unchanged
+                                    * since the previous tb_mcmc_steps call of this mutation (skip constant reloads) */
   double beta;
   uint64_t seed, iteration;         /* Philox key material */
   int64_t slot_offset;              /* global slot id of local walker 0 (multi-GPU) */
@@ -279,6 +284,10 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
 int tb_search_right_sharded(const double* cdf, int64_t n, const int64_t* seg_begin, const double* seg_shift,
                             const double* seg_start, int32_t n_seg, double total, const double* draws,
                             int64_t m, int64_t* idx, tb_stream_t stream);
+/* the same with a guide table (tb_search_guide_bytes(bits) bytes): identical indices, ~3 probes per draw */
+int tb_search_right_sharded_guided(const double* cdf, int64_t n, const int64_t* seg_begin, const double* seg_shift,
+                                   const double* seg_start, int32_t n_seg, double total, const double* draws,
+                                   int64_t m, void* guide, int32_t bits, int64_t* idx, tb_stream_t stream);
 /* w /= denom */
 int tb_scale_inplace(double* w, int64_t n, double denom, tb_stream_t stream);
 /* one stage of tb_select_ranks: 0 init, 1 local histogram of `level`, 2 pick from the (all-reduced)

@@ -334,7 +334,8 @@ int launch_fast_variant(const StepArgs& a, int count, cudaStream_t st) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  if (KONE) {   // device -> constant copies, ordered on the stream before the step launches
+  if (KONE && !a.p.reserved) {   // device -> constant copies, ordered on the stream before the step launches
+                                 // (reserved != 0: the caller states they are unchanged since its last call)
     const cudaMemcpyKind kd = cudaMemcpyDeviceToDevice;
     cudaMemcpyToSymbolAsync(c_mode, a.p.mode_mean, sizeof(double) * D, 0, kd, st);
     cudaMemcpyToSymbolAsync(c_mode, a.p.mode_chol, sizeof(double) * D * D, sizeof(double) * D, kd, st);

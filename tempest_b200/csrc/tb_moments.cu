@@ -123,6 +123,35 @@ binade_hist_kernel(const double* __restrict__ w, int64_t n, unsigned long long* 
   }
 }
 
+// second level: the 2048 linear sub-bins (top 11 mantissa bits) of ONE binade, same three sums per bin.
+// Narrows the trim bracket from a binade to 1/2048 of it, so that only the one or two percentile grid
+// points inside the flipping sub-bin need an exact evaluation.
+__global__ void __launch_bounds__(kBlock)
+subbin_hist_kernel(const double* __restrict__ w, int64_t n, int binade, unsigned long long* __restrict__ gcount,
+                   double* __restrict__ gs1, double* __restrict__ gs2) {
+  __shared__ unsigned int cnt[2048];
+  __shared__ double s1[2048];
+  __shared__ double s2[2048];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) { cnt[i] = 0u; s1[i] = 0.0; s2[i] = 0.0; }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = __ldg(w + i);
+    const long long bits = __double_as_longlong(v);
+    if ((int)((bits >> 52) & 0x7ff) != binade) continue;
+    const int sub = (int)((bits >> 41) & 0x7ff);
+    atomicAdd(&cnt[sub], 1u); atomicAdd(&s1[sub], v); atomicAdd(&s2[sub], v * v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+    if (cnt[i]) {
+      atomicAdd(&gcount[i], (unsigned long long)cnt[i]);
+      atomicAdd(&gs1[i], s1[i]);
+      atomicAdd(&gs2[i], s2[i]);
+    }
+  }
+}
+
 // ---- ordered compaction of {w >= thr} ---------------------------------------------------
 constexpr int kCompactItems = 2048;  // elements per CTA
 __global__ void __launch_bounds__(kBlock)
@@ -969,6 +998,19 @@ int tb_binade_hist(const double* w, int64_t n, uint64_t* count2048, double* s1_2
   cudaMemsetAsync(s2_2048, 0, 2048 * sizeof(double), st);
   const int grid = stream_grid(n, kBlock * 8, 4);
   binade_hist_kernel<<<grid, kBlock, 0, st>>>(w, n, (unsigned long long*)count2048, s1_2048, s2_2048);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_subbin_hist(const double* w, int64_t n, int32_t binade, uint64_t* count2048, double* s1_2048, double* s2_2048,
+                   tb_stream_t stream) {
+  if (n <= 0 || !w || !count2048 || !s1_2048 || !s2_2048 || binade < 0 || binade > 2047) return TB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(count2048, 0, 2048 * sizeof(uint64_t), st);
+  cudaMemsetAsync(s1_2048, 0, 2048 * sizeof(double), st);
+  cudaMemsetAsync(s2_2048, 0, 2048 * sizeof(double), st);
+  const int grid = stream_grid(n, kBlock * 8, 4);
+  subbin_hist_kernel<<<grid, kBlock, 0, st>>>(w, n, binade, (unsigned long long*)count2048, s1_2048, s2_2048);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

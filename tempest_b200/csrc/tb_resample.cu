@@ -437,6 +437,55 @@ search_right_sharded_kernel(const double* __restrict__ cdf, int64_t n, const int
   }
 }
 
+// guide table for the sharded search: guide[g] = first local j whose GLOBAL cdf value / total exceeds g/G
+__global__ void __launch_bounds__(kBlock)
+search_sharded_guide_kernel(const double* __restrict__ cdf, int64_t n, const int64_t* __restrict__ seg_begin,
+                            const double* __restrict__ seg_shift, int S, double total, int64_t G,
+                            int64_t* __restrict__ guide) {
+  const double invG = 1.0 / (double)G;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= G; g += stride) {
+    if (g == G) { guide[g] = n; continue; }
+    const double u = (double)g * invG;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int s = seg_of(seg_begin, S, mid);
+      if (__ddiv_rn(__dadd_rn(__ldg(cdf + mid), __ldg(seg_shift + s)), total) <= u) lo = mid + 1; else hi = mid;
+    }
+    guide[g] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+search_right_sharded_guided_kernel(const double* __restrict__ cdf, int64_t n, const int64_t* __restrict__ seg_begin,
+                                   const double* __restrict__ seg_shift, const double* __restrict__ seg_start, int S,
+                                   double total, const double* __restrict__ draws, int64_t m,
+                                   const int64_t* __restrict__ guide, int64_t G, int64_t* __restrict__ idx) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+    const double u = __ldg(draws + k);
+    int64_t lo = 0, hi = n;
+    if (u >= 0.0 && u < 1.0) {
+      int64_t g = (int64_t)(u * (double)G);
+      if (g > G - 1) g = G - 1;
+      lo = __ldg(guide + g);
+      hi = __ldg(guide + g + 1);
+    }
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int s = seg_of(seg_begin, S, mid);
+      if (__ddiv_rn(__dadd_rn(__ldg(cdf + mid), __ldg(seg_shift + s)), total) <= u) lo = mid + 1; else hi = mid;
+    }
+    bool mine = lo < n;
+    if (mine) {
+      const int s = seg_of(seg_begin, S, lo);
+      if (lo == __ldg(seg_begin + s)) mine = __ddiv_rn(__ldg(seg_start + s), total) <= u;
+    }
+    idx[k] = mine ? lo : -1;
+  }
+}
+
 __global__ void __launch_bounds__(kBlock)
 systematic_kernel(const double* __restrict__ cdf, int64_t n, double u0, int64_t m, int64_t* __restrict__ idx,
                   int* __restrict__ overflow) {
@@ -532,6 +581,23 @@ int tb_search_right_sharded(const double* cdf, int64_t n, const int64_t* seg_beg
   if (m == 0) return TB_OK;
   search_right_sharded_kernel<<<stream_grid(m, kBlock, 16), kBlock, 0, as_stream(stream)>>>(
       cdf, n, seg_begin, seg_shift, seg_start, n_seg, total, draws, m, idx);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_search_right_sharded_guided(const double* cdf, int64_t n, const int64_t* seg_begin, const double* seg_shift,
+                                   const double* seg_start, int32_t n_seg, double total, const double* draws,
+                                   int64_t m, void* guide, int32_t bits, int64_t* idx, tb_stream_t stream) {
+  if (n <= 0 || m < 0 || n_seg <= 0 || !cdf || !seg_begin || !seg_shift || !seg_start || !guide || bits < 4 || bits > 24 ||
+      (m > 0 && (!draws || !idx)))
+    return TB_ERR_ARG;
+  if (m == 0) return TB_OK;
+  const int64_t G = (int64_t)1 << bits;
+  cudaStream_t st = as_stream(stream);
+  search_sharded_guide_kernel<<<stream_grid(G + 1, kBlock, 16), kBlock, 0, st>>>(cdf, n, seg_begin, seg_shift, n_seg, total,
+                                                                                G, (int64_t*)guide);
+  search_right_sharded_guided_kernel<<<stream_grid(m, kBlock, 16), kBlock, 0, st>>>(
+      cdf, n, seg_begin, seg_shift, seg_start, n_seg, total, draws, m, (const int64_t*)guide, G, idx);
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

@@ -107,6 +107,20 @@ class ShardedKernels(Kernels):
             self.comm.allreduce_sum_(t)
         return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
 
+    def g_subhist(self, w, n: int, binade: int):
+        cnt = self.ws.i64("trim_cnt2", 2048)
+        s1 = self.ws.f64("trim_s1b", 2048)
+        s2 = self.ws.f64("trim_s2b", 2048)
+        if n > 0:
+            _lib.check(self.lib.tb_subbin_hist(ptr(w), n, int(binade), ptr(cnt), ptr(s1), ptr(s2), stream_ptr()),
+                       "tb_subbin_hist")
+        else:
+            for t in (cnt, s1, s2):
+                t.zero_()
+        for t in (cnt, s1, s2):
+            self.comm.allreduce_sum_(t)
+        return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
+
     def g_select(self, base, rows, stride, m, ncols, mult, ranks, nranks, out):
         """Distributed radix select: local histograms, all-reduced per level, replicated picks."""
         lib = self.lib
@@ -194,8 +208,16 @@ class ShardedKernels(Kernels):
             return out, total
         seg_start = torch.as_tensor(start, dtype=F64).to(self.device)
         seg_shift = seg_start - before
+        m = int(draws.numel())
+        if m >= 1 << 16 and n >= 1 << 12:
+            bits = max(10, min(20, (m // 8).bit_length() - 1))
+            guide = self.ws.bytes("search_guide", self.lib.tb_search_guide_bytes(bits))
+            _lib.check(self.lib.tb_search_right_sharded_guided(ptr(cdf), n, ptr(seg_begin), ptr(seg_shift),
+                                                               ptr(seg_start), S, total, ptr(draws), m, ptr(guide), bits,
+                                                               ptr(out), stream_ptr()), "tb_search_right_sharded_guided")
+            return out, total
         _lib.check(self.lib.tb_search_right_sharded(ptr(cdf), n, ptr(seg_begin), ptr(seg_shift), ptr(seg_start), S,
-                                                    total, ptr(draws), draws.numel(), ptr(out), stream_ptr()),
+                                                    total, ptr(draws), m, ptr(out), stream_ptr()),
                    "tb_search_right_sharded")
         return out, total
 

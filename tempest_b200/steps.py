@@ -252,6 +252,14 @@ class Kernels:
         _lib.check(self.lib.tb_binade_hist(ptr(w), n, ptr(cnt), ptr(s1), ptr(s2), stream_ptr()), "tb_binade_hist")
         return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
 
+    def g_subhist(self, w: torch.Tensor, n: int, binade: int):
+        cnt = self.ws.i64("trim_cnt2", 2048)
+        s1 = self.ws.f64("trim_s1b", 2048)
+        s2 = self.ws.f64("trim_s2b", 2048)
+        _lib.check(self.lib.tb_subbin_hist(ptr(w), n, int(binade), ptr(cnt), ptr(s1), ptr(s2), stream_ptr()),
+                   "tb_subbin_hist")
+        return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
+
     def g_sum3(self, vals: torch.Tensor, m: int, thr: float):
         """(count, sum w, sum w^2) over w >= thr."""
         out3 = self.ws.f64("trim_m3", 3)
@@ -310,6 +318,22 @@ class Kernels:
         bin_hi = np.searchsorted(cnt_lt, hi_arr, side="right") - 1
         sure_true = bin_hi < bstar
         sure_false = bin_lo > bstar
+        fine_edge = None
+        if np.count_nonzero(~sure_true & ~sure_false) > 2 and 0 < bstar < 2047:
+            # second level: 2048 linear sub-bins of binade bstar narrow the bracket to one sub-bin
+            f_cnt, f_s1, f_s2 = self.g_subhist(w, n, bstar)
+            a1 = (s1_ge[bstar + 1] if bstar + 1 < 2048 else 0.0) + np.cumsum(f_s1[::-1])[::-1]
+            a2 = (s2_ge[bstar + 1] if bstar + 1 < 2048 else 0.0) + np.cumsum(f_s2[::-1])[::-1]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                f_ok = np.nan_to_num((a1 * a1 / a2) / ess_total, nan=0.0) >= ess
+            if f_ok.any() and int(f_cnt.sum()) == int(h_cnt[bstar]):
+                kstar = int(np.max(np.nonzero(f_ok)[0]))         # highest sub-bin edge that still passes
+                f_lt = cnt_lt[bstar] + np.concatenate([[0], np.cumsum(f_cnt)])   # elements below sub-edge k
+                f_lo = np.searchsorted(f_lt, lo_arr, side="right") - 1
+                f_hi = np.searchsorted(f_lt, hi_arr, side="right") - 1
+                sure_true = sure_true | ((bin_hi == bstar) & (f_hi < kstar))
+                sure_false = sure_false | ((bin_lo == bstar) & (f_lo > kstar))
+                fine_edge = (f_lo, kstar)
         amb = np.nonzero(~sure_true & ~sure_false)[0]
         best = int(np.max(np.nonzero(sure_true)[0])) if sure_true.any() else 0
         cand = np.union1d(amb, [best]).astype(np.int64)   # grid points that may need an exact evaluation
@@ -332,6 +356,10 @@ class Kernels:
                     comp = (w, n, 0)
                 else:
                     edge = float(np.ldexp(1.0, b0 - 1023))
+                    if fine_edge is not None and b0 == bstar:
+                        # every candidate rank lies at or above this sub-bin edge of binade bstar
+                        k0 = int(fine_edge[0][cand][bin_lo[cand] == bstar].min())
+                        edge = float(np.ldexp(1.0 + max(k0, 0) / 2048.0, bstar - 1023))
                     comp_lo = edge
                     wc = self.ws.f64("trim_comp", n)
                     nout = self.ws.i64("trim_nout", 1)
@@ -860,6 +888,7 @@ class Mutator:
             if budget > 0:
                 _lib.check(lib.tb_mcmc_steps(n, C.byref(params), tape_ref, ptr(assign), ptr(u), ptr(logl), ptr(qcur),
                                              ptr(ws), ptr(ctrl), int(budget), sp), "tb_mcmc_steps")
+                params.reserved = 1                    # same mode statistics for the rest of this mutation
                 launched += budget
             h = ctrl.cpu().numpy()
             if h[1] != 0.0 or launched >= n_cap:
@@ -867,7 +896,7 @@ class Mutator:
             if tape is not None and launched >= tape.steps:
                 raise RuntimeError(
                     f"tape holds {tape.steps} MCMC steps but the device stop rule has not fired after {launched}")
-            budget = min(self.CHUNK, n_cap - launched)
+            budget = min(self.CHUNK * (2 if fused else 1), n_cap - launched)   # steps are short when sharded
         core.n_mcmc_launches += launched
         if fused and not core.bridge.external:
             k.consume_exchanges(int(h[0]))                         # one exchange per executed step
