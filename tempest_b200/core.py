@@ -86,6 +86,13 @@ class SamplerCore:
                 min_points=None if cap is None else 4 * config.n_dim,
                 threshold_modifier=config.split_threshold, covariance_type="full", verbose=False,
                 normalize=config.normalize)
+        # independent branches of one iteration run on a side stream (single GPU, ESS mode, one mode,
+        # multinomial resampling): the cv diagnostic and the resampling overlap with the Trainer
+        self.overlap = (not self.comm.on and config.volume_variation is None and not config.clustering
+                        and config.resample == "mult")
+        self.side = torch.cuda.Stream(self.device) if self.overlap else None
+        self.k_side = Kernels(self.device) if self.overlap else None
+        self._cv_pending = None
         self.reweighter = Reweighter(self)
         self.trainer = Trainer(self)
         self.resampler = Resampler(self)
@@ -146,6 +153,34 @@ class SamplerCore:
             p.mode_dof = mode_stats.degrees_of_freedom.data_ptr()
         p.bc_kind = self._bc.data_ptr() if self._bc is not None else None
         return p
+
+    # -- cv diagnostic on the side stream (reweight.py:417-419 computes it inline) -----------------------
+    def begin_cv(self, w: torch.Tensor) -> None:
+        ens = self.ensemble
+        n, d = ens.n_total, ens.n_dim
+        ks = self.k_side
+        ks.ws.hint = ens.cap
+        w_cv = ks.ws.f64("cv_w", n)
+        w_cv.copy_(w)                       # trim_weights renormalises w in place; cv uses the weights as they are now
+        ready = torch.cuda.Event()
+        ready.record()
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            ks.volume_variation_begin(ens.u, w_cv, n, d)
+        self._cv_pending = (w_cv, n)
+
+    def mid_cv(self) -> None:
+        if self._cv_pending is not None:
+            w_cv, n = self._cv_pending
+            with torch.cuda.stream(self.side):
+                self.k_side.volume_variation_mid(self.ensemble.u, w_cv, n, self.ensemble.n_dim)
+
+    def end_cv(self) -> None:
+        if self._cv_pending is not None:
+            self._cv_pending = None
+            with torch.cuda.stream(self.side):
+                cv = self.k_side.volume_variation_end()
+            self.state.set_current("cv", cv)
 
     def transform_to_x(self, u: torch.Tensor) -> torch.Tensor:
         """x = prior_transform(u): tb_transform for registry priors, the user's callable otherwise."""
@@ -214,10 +249,12 @@ class SamplerCore:
         weights = self.reweighter.run()
         self._stage("train")
         mode_stats = self.trainer.run(weights)
+        self.mid_cv()
         self._stage("resample")
         self.resampler.run(weights)
         self._stage("mutate")
         self.mutator.run(mode_stats)
+        self.end_cv()
         self._stage("commit")
         # commit (state_manager.py:356-416): particles to the device ensemble, scalars to host lists
         st = self.state

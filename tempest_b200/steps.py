@@ -174,8 +174,17 @@ class Kernels:
     # -- moments / cv -------------------------------------------------------------------
     def volume_variation(self, u: torch.Tensor, w: torch.Tensor, n: int, d: int) -> float:
         """tools.py:58-117 on the device (w already normalised)."""
+        self.volume_variation_begin(u, w, n, d)
+        self.volume_variation_mid(u, w, n, d)
+        return self.volume_variation_end()
+
+    # The three phases can be issued on a side stream around other host work: `begin` only enqueues
+    # (weighted moments + Cholesky), `mid` takes the rank decision on the host and enqueues the
+    # Mahalanobis pass, `end` reads the scalar.
+    def volume_variation_begin(self, u: torch.Tensor, w: torch.Tensor, n: int, d: int) -> None:
+        self._vv_state = "small" if n < d + 1 else "begun"
         if n < d + 1:
-            return 1e10
+            return
         ws = self.ws.bytes("mom", self.lib.tb_moments_workspace_bytes(d))
         mean = self.ws.f64("vv_mean", d)
         cov = self.ws.f64("vv_cov", d * d)
@@ -185,10 +194,21 @@ class Kernels:
         inv = self.ws.f64("vv_inv", d * d)
         info = self.ws.i32("vv_info", 1)
         norms = self.ws.f64("vv_norms", 3)
+        work.copy_(cov)
+        _lib.check(self.lib.tb_chol_inv(ptr(work), d, 1, None, ptr(inv), ptr(info), ptr(norms), stream_ptr()),
+                   "tb_chol_inv")
+
+    def volume_variation_mid(self, u: torch.Tensor, w: torch.Tensor, n: int, d: int) -> None:
+        if self._vv_state != "begun":
+            return
+        mean, cov = self.ws.f64("vv_mean", d), self.ws.f64("vv_cov", d * d)
+        work, inv = self.ws.f64("vv_work", d * d), self.ws.f64("vv_inv", d * d)
+        info, norms = self.ws.i32("vv_info", 1), self.ws.f64("vv_norms", 3)
         for attempt in range(2):
-            work.copy_(cov)
-            _lib.check(self.lib.tb_chol_inv(ptr(work), d, 1, None, ptr(inv), ptr(info), ptr(norms), stream_ptr()),
-                       "tb_chol_inv")
+            if attempt == 1:
+                work.copy_(cov)
+                _lib.check(self.lib.tb_chol_inv(ptr(work), d, 1, None, ptr(inv), ptr(info), ptr(norms), stream_ptr()),
+                           "tb_chol_inv")
             code = int(info.item())
             nr = norms.cpu().numpy()
             # matrix_rank(cov) < d  <=>  cond_2 >= 1/(d*eps); |A|_F |A^-1|_F >= cond_2 screens it
@@ -199,12 +219,18 @@ class Kernels:
             if not singular:
                 break
             if attempt == 1:
-                return 1e10
+                self._vv_state = "singular"
+                return
             _lib.check(self.lib.tb_add_trace_reg(ptr(cov), d, 1e-6, stream_ptr()), "tb_add_trace_reg")
         out = self.ws.f64("vv_out", 2)
         _lib.check(self.lib.tb_mahalanobis_cv(ptr(u), ptr(w), n, d, ptr(mean), ptr(inv), ptr(self._reduce_ws),
                                               ptr(out), stream_ptr()), "tb_mahalanobis_cv")
-        return float(out[0].item())
+        self._vv_state = "enqueued"
+
+    def volume_variation_end(self) -> float:
+        if self._vv_state in ("small", "singular"):
+            return 1e10
+        return float(self.ws.f64("vv_out", 2)[0].item())
 
     # -- resampling -----------------------------------------------------------------------
     def cdf(self, p: torch.Tensor, n: int, name: str = "cdf") -> torch.Tensor:
@@ -287,7 +313,7 @@ class Kernels:
         return out
 
     # -- trim_weights (tools.py:10-55) ------------------------------------------------------
-    def trim(self, w: torch.Tensor, n: int, ess: float = TRIM_ESS, bins: int = TRIM_BINS):
+    def trim(self, w: torch.Tensor, n: int, ess: float = TRIM_ESS, bins: int = TRIM_BINS, after_normalize=None):
         """Normalises ``w`` IN PLACE (tools.py:36) and returns (idx int64[n_trim], w_trim[n_trim]).
 
         The reference scans i = bins-1 .. 0, each time thresholding at np.percentile(w, p_i) and
@@ -299,6 +325,8 @@ class Kernels:
         lib = self.lib
         st = stream_ptr()
         _, sumsq = self.g_normalize(w, n)
+        if after_normalize is not None:
+            after_normalize()                 # w is final from here on (read-only below)
         h_cnt, h_s1, h_s2 = self.g_hist(w, n)
         n_glob = self.g_int(n)
         ess_total = 1.0 / sumsq
@@ -560,7 +588,11 @@ class Reweighter:
             stats = k.probe_out                     # (m, S1, ..., logZ) of the last probe == probe(beta)
         core._stage("reweight:cv")
         w = k.weights(ens, beta, stats, core.weights_buffer())
-        cv = k.volume_variation(ens.u, w, ens.n_total, ens.n_dim)     # reweight.py:417-419
+        if core.overlap:
+            core.begin_cv(w)                                          # side stream; finished before the commit
+            cv = None
+        else:
+            cv = k.volume_variation(ens.u, w, ens.n_total, ens.n_dim)     # reweight.py:417-419
         logz = float(stats[4].item())
         st.update_current({"logz": logz, "beta": float(beta), "ess": float(ess), "cv": cv})
         return w
@@ -608,7 +640,8 @@ class Trainer:
         lib = k.lib
         st = stream_ptr()
         core._stage("train:trim")
-        idx, wt = k.trim(weights, ens.n_total)
+        hook = (lambda: core.resampler.begin_async(weights)) if core.overlap else None
+        idx, wt = k.trim(weights, ens.n_total, after_normalize=hook)
         core._stage("train:draws")
         core.trace["trim_idx"], core.trace["trim_w"] = idx, wt
         n_trim = int(idx.numel())                       # local; equals the global count on one GPU
@@ -734,6 +767,30 @@ class Resampler:
 
     def __init__(self, core):
         self.core = weakref.proxy(core)      # the core owns the steps; no reference cycle, so memory frees on del
+        self._pending = None
+
+    def begin_async(self, weights: torch.Tensor) -> None:
+        """Multinomial resampling on the side stream, issued as soon as trim_weights has normalised the
+        weights in place (tools.py:36) -- from then on they are read-only -- so the cumulative sum, the
+        search and the row gather overlap with the rest of the Trainer on the main stream."""
+        core = self.core
+        ens = core.ensemble
+        n, d = core.n_local, ens.n_dim
+        ready = torch.cuda.Event()
+        ready.record()
+        u = torch.empty((n, d), dtype=F64, device=core.device)          # allocated (and later consumed) on the main stream
+        logl = torch.empty(n, dtype=F64, device=core.device)
+        core.side.wait_event(ready)
+        with torch.cuda.stream(core.side):
+            ks = core.k_side
+            cdf = ks.cdf(weights, ens.n_total)
+            idx = ks.ws.i64("res_idx", n)
+            ks.search_right(cdf, ens.n_total, core.rng.resample_u(n), idx)
+            _lib.check(ks.lib.tb_gather_rows(ptr(ens.u), ptr(ens.logl), d, ptr(idx), n, ptr(u), ptr(logl),
+                                             stream_ptr()), "tb_gather_rows")
+            done = torch.cuda.Event()
+            done.record()
+        self._pending = (u, logl, idx, done)
 
     def run(self, weights: Optional[torch.Tensor]) -> None:
         core = self.core
@@ -744,6 +801,14 @@ class Resampler:
             return
         ens = core.ensemble
         k = core.k
+        if self._pending is not None:
+            u, logl, idx, done = self._pending
+            self._pending = None
+            torch.cuda.current_stream().wait_event(done)
+            core.trace["resample_idx"] = idx
+            core.assign = None
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
+            return
         if k.sharded:
             if core.config.resample != "mult":
                 raise NotImplementedError("systematic resampling is not sharded yet; use resample='mult' on >1 GPU")

@@ -1,0 +1,146 @@
+"""BASELINE.json configurations at their FULL sizes, checked through size-independent properties
+(the oracle cannot run these in seconds): monotone temperature ladder, termination rule, evidence,
+normalised weights, sorted cumulative sums, valid / idempotent resampling, symmetric moments.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def test_c4_rosenbrock_2pow20_run_properties():
+    """configs[3]: 10-D Rosenbrock, 2^20 particles (the headline run)."""
+    import tempest_b200 as tp
+
+    n, d = 1 << 20, 10
+    s = tp.Sampler(tp.UniformPrior(-10.0, 10.0, d), tp.Rosenbrock(d), d, n_particles=n, vectorize=True,
+                   clustering=False, random_state=20261018)
+    s.run(progress=False)
+    st = s.state
+    beta = st.get_history("beta")
+    T = len(beta)
+    assert T >= 30 and np.all(np.diff(beta) >= 0) and beta[-1] == 1.0 and np.count_nonzero(beta == 0.0) == 3
+    steps = st.get_history("steps")
+    assert np.all(steps[3:] >= 1 * d) and np.all(steps <= 20 * d)               # mcmc.py:104-135 bounds
+    calls = st.get_history("calls")
+    assert calls[-1] == n * (3 + int(steps[3:].sum()))                            # mutate.py:106, mcmc.py:89
+    ess = st.get_history("ess")
+    assert np.all(ess[4:] >= 0.98 * 2.0 * n) and np.all(ess[4:-1] <= 1.02 * 2.0 * n)   # bisection lands on the target
+    logz = s.evidence()[0]
+    # quadrature gives -29.996; the algorithm itself (oracle at small N: -29.6 +- 0.3) sits slightly above it
+    assert -30.2 < logz < -29.6
+    x, w, logl = s.posterior()
+    assert w.sum() == pytest.approx(1.0, abs=1e-9) and np.all(w > 0) and x.shape == (w.size, d)
+    assert np.all(np.abs(x) <= 10.0)
+    m = np.average(x, axis=0, weights=w)
+    np.testing.assert_allclose(m[0::2], 1.0, atol=0.05)                            # E[x_even] = 1
+    np.testing.assert_allclose(m[1::2], 1.5, atol=0.08)                            # E[x_odd] = E[x^2] = 1 + 1/2
+    # same seed -> same run, bit for bit (counter-based RNG, order-fixed reductions)
+    s2 = tp.Sampler(tp.UniformPrior(-10.0, 10.0, d), tp.Rosenbrock(d), d, n_particles=n, vectorize=True,
+                    clustering=False, random_state=20261018)
+    s2.run(progress=False)
+    assert s2.evidence()[0] == logz
+    np.testing.assert_array_equal(s2.state.get_history("beta"), beta)
+
+
+def test_c2_mixture_2pow16_clustered_run():
+    """configs[1]: 2-D four-component mixture, 2^16 particles, clustering on; logZ = -log 400."""
+    import tempest_b200 as tp
+
+    s = tp.Sampler(tp.UniformPrior(-10.0, 10.0, 2), tp.IsotropicMixture.four_corners(2), 2, n_particles=1 << 16,
+                   vectorize=True, clustering=True, random_state=7)
+    s.run(progress=False)
+    assert s.evidence()[0] == pytest.approx(-np.log(400.0), abs=0.02)
+    x, w, _ = s.posterior()
+    for sx in (-1, 1):
+        for sy in (-1, 1):
+            assert w[(np.sign(x[:, 0]) == sx) & (np.sign(x[:, 1]) == sy)].sum() == pytest.approx(0.25, abs=0.02)
+
+
+def test_c5_shells_2pow22_persistent_ensemble_kernels():
+    """configs[4]: 100-D twin shells, 2^22 persistent particles: the HBM-bound reweighting / resampling /
+    moment kernels at full size, through properties that need no CPU replay."""
+    import tempest_b200 as tp
+    from tempest_b200 import _lib
+    from tempest_b200.ensemble import PersistentEnsemble, ptr, stream_ptr
+    from tempest_b200.steps import Kernels
+
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    k = Kernels(dev)
+    d, n_gen, T = 100, 1 << 17, 32
+    like = tp.TwinShells(d)
+    prior = tp.UniformPrior(-6.0, 6.0, d)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    ens = PersistentEnsemble(d, dev)
+    params = _lib.TbMcmcParams()
+    params.n_dim, params.n_modes, params.like_id, params.prior_id = d, 1, like.kernel_id, prior.kernel_id
+    lp = torch.as_tensor(like.dparams(), dtype=torch.float64).to(dev)
+    pp = torch.as_tensor(prior.dparams(), dtype=torch.float64).to(dev)
+    params.like_params, params.prior_params = lp.data_ptr(), pp.data_ptr()
+    betas = [0.0, 0.0, 0.0] + list(np.geomspace(1e-6, 1.0, T - 3))
+    logz = 0.0
+    for t in range(T):
+        # particles concentrated towards the shells as beta grows (synthetic)
+        u = torch.rand((n_gen, d), dtype=torch.float64, device=dev, generator=g)
+        logl = torch.empty(n_gen, dtype=torch.float64, device=dev)
+        _lib.check(lib.tb_transform(ptr(u), n_gen, C.byref(params), None, ptr(logl), stream_ptr()), "tb_transform")
+        ens.append(u, logl, betas[t], logz)
+        logz -= 0.5
+    n = ens.n_total
+    assert n == 1 << 22
+    # incremental mixture column == full rebuild, bit for bit
+    c_inc = ens.C[:n].clone()
+    ens.rebuild_mixture()
+    assert torch.equal(c_inc, ens.C[:n])
+    # probe / weights: normalised, ESS consistent with the weights themselves
+    beta = 0.5 * betas[-4]
+    out = k.probe(ens, beta).clone()
+    w = torch.empty(n, dtype=torch.float64, device=dev)
+    k.weights(ens, beta, out, w)
+    assert float(w.sum()) == pytest.approx(1.0, abs=1e-12)
+    assert float(out[3]) == pytest.approx(1.0 / float((w * w).sum()), rel=1e-10)
+    # exact cumulative sum: non-decreasing, ends at the (sequential) total, first element = w_0
+    cdf = k.cdf(w, n, "fs_cdf")
+    assert bool((cdf[1:] >= cdf[:-1]).all()) and float(cdf[0]) == float(w[0])
+    assert float(cdf[-1]) == pytest.approx(1.0, abs=1e-12)
+    # multinomial indices: valid, consistent with the cdf, idempotent; guided == plain search
+    m = 1 << 20
+    draws = torch.rand(m, dtype=torch.float64, device=dev, generator=g)
+    idx = torch.empty(m, dtype=torch.int64, device=dev)
+    k.search_right(cdf, n, draws, idx)
+    plain = torch.empty_like(idx)
+    _lib.check(lib.tb_search_right(ptr(cdf), n, ptr(draws), m, ptr(plain), stream_ptr()), "tb_search_right")
+    assert torch.equal(idx, plain)
+    assert int(idx.min()) >= 0 and int(idx.max()) < n
+    scaled = cdf / cdf[-1]
+    assert bool((scaled[idx] > draws).all())
+    prev = torch.where(idx > 0, scaled[(idx - 1).clamp(min=0)], torch.zeros_like(draws))
+    assert bool((prev <= draws).all())
+    # gather: rows come back unchanged
+    au = torch.empty((m, d), dtype=torch.float64, device=dev)
+    al = torch.empty(m, dtype=torch.float64, device=dev)
+    _lib.check(lib.tb_gather_rows(ptr(ens.u), ptr(ens.logl), d, ptr(idx), m, ptr(au), ptr(al), stream_ptr()), "gather")
+    probe_rows = torch.randint(0, m, (64,), device=dev)
+    assert torch.equal(au[probe_rows], ens.u[idx[probe_rows]]) and torch.equal(al[probe_rows], ens.logl[idx[probe_rows]])
+    # weighted moments at d = 100: symmetric covariance, mean inside the unit cube, cv finite
+    cv = k.volume_variation(ens.u, w, n, d)
+    assert np.isfinite(cv) and cv >= 0.0
+    cov = k.ws.f64("vv_cov", d * d).reshape(d, d)
+    assert torch.equal(cov, cov.T)
+    mean = k.ws.f64("vv_mean", d)
+    assert bool(((mean > 0.0) & (mean < 1.0)).all())
+    # trimming keeps the heaviest weights and (almost) all of the effective sample size
+    w2 = w.clone()
+    tidx, wt = k.trim(w2, n)
+    assert float(wt.sum()) == pytest.approx(1.0, abs=1e-12)
+    assert int(tidx.numel()) <= n and bool((tidx[1:] > tidx[:-1]).all())
+    kept_min = float(w2[tidx].min())
+    mask = torch.ones(n, dtype=torch.bool, device=dev)
+    mask[tidx] = False
+    assert float(w2[mask].max()) <= kept_min if int(mask.sum()) else True
+    assert (1.0 / float((wt * wt).sum())) >= 0.99 * (1.0 / float((w2 * w2).sum())) * (1 - 1e-12)
