@@ -211,7 +211,7 @@ def main():
     # ---- untimed library warm-up: one complete run loads every kernel module (CUDA lazy loading), sizes the
     #      NCCL channels and fills the allocator pools ("exclude one untimed warm-up run") ----------
     ws_ = tp.Sampler(tp.UniformPrior(-10.0, 10.0, N_DIM), tp.Rosenbrock(N_DIM), N_DIM, n_particles=n_particles,
-                     vectorize=True, clustering=False, random_state=1)
+                     vectorize=True, clustering=False, random_state=SEED)
     ws_.run(n_total=4096, progress=False)      # same shape as the timed workload: the caching allocator keeps its blocks
     _ = ws_.posterior()                        # ... and the page-locked staging blocks of the posterior read-back
     del ws_, _
@@ -229,10 +229,7 @@ def main():
         nonlocal s, core
         if not core._not_termination():
             runs_T.append(core.state.get_history_length())
-            s = new_sampler()
-            core = s._core
-            core.profile = args.profile_stages
-            core._initialize_fresh()
+            core.reset()                       # next run: same sampler, same buffers, history cleared
             core.n_total = 4096
         core.execute_iteration(export=False)
 

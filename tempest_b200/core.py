@@ -208,6 +208,22 @@ class SamplerCore:
         return logw, float(h[4])
 
     # -- the PS loop ----------------------------------------------------------------------------
+    def reset(self) -> None:
+        """Forget the history but keep every device buffer (a fresh run on the same allocation; the
+        reference needs a new Sampler for that because run() never clears its history, core.py:376-381)."""
+        ens = self.ensemble
+        ens.n_total = 0
+        ens.gen_beta, ens.gen_logz, ens.gen_n, ens.gen_n_local = [], [], [], []
+        st = self.state
+        for key in st._history:
+            st._history[key] = []
+        for key in list(st._current):
+            st._current[key] = None
+        self.assign = None
+        self._cv_pending = None
+        self.trace = {}
+        self._initialize_fresh()
+
     def _initialize_fresh(self) -> None:                 # core.py:376-381 (history is NOT cleared)
         self.state.update_current({"iter": 0, "calls": 0, "beta": 0.0, "logz": 0.0})
 

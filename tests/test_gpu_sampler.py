@@ -487,3 +487,25 @@ def test_checkpoint_resume_reproduces_the_uninterrupted_run(tmp_path):
     np.testing.assert_array_equal(wa, wc)
     res = c.results()
     assert res["logw"].shape == (T * 512,) and res["u"].shape == (T, 512, 4)
+
+
+def test_core_reset_reruns_on_the_same_buffers():
+    """SamplerCore.reset() (used by bench.py between runs): history cleared, device buffers kept, and the
+    rerun reproduces the first run bit for bit."""
+    import tempest_b200 as tp
+
+    s = tp.Sampler(tp.UniformPrior(-10.0, 10.0, 4), tp.Rosenbrock(4), 4, n_particles=2048, vectorize=True,
+                   clustering=False, random_state=23)
+    s.run(n_total=1024, progress=False)
+    beta, logz, u_last = s.state.get_history("beta"), s.evidence()[0], s.state.get_history("u")[-1]
+    ptr_before = s._core.ensemble.u.data_ptr()
+    s._core.reset()
+    assert s.state.get_history_length() == 0 and s._core.ensemble.n_total == 0
+    s._core.n_total = 1024
+    while s._core._not_termination():
+        s._core.execute_iteration(export=False)
+    s._core.state.set_current("logz", float(s._core._last_posterior_probe[4]))
+    assert s._core.ensemble.u.data_ptr() == ptr_before
+    np.testing.assert_array_equal(s.state.get_history("beta"), beta)
+    np.testing.assert_array_equal(s.state.get_history("u")[-1], u_last)
+    assert s.evidence()[0] == logz
