@@ -98,6 +98,27 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 (NCCL prints its version
+    there), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(text: str) -> None:
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def peak_hbm_gbs() -> tuple:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -174,9 +195,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-stages", action="store_true")
     args = ap.parse_args()
+    _quiet_stdout()
 
     if args.impl == "reference":
-        print(json.dumps(run_reference_arm(args)))
+        _emit(json.dumps(run_reference_arm(args)))
         return
 
     import numpy as np
@@ -370,7 +392,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms,
         }
         line["gpu_launches"] = int(launches)
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
