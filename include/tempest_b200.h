@@ -184,6 +184,15 @@ int tb_select_pair(const double* base, const int64_t* rows, int64_t stride, int6
  * histogram -> compaction of the bucket(s) holding the two ranks -> exact in-block select.
  * *overflow = 1 when a bucket held more than 65536 candidates (caller falls back to tb_select_pair). */
 size_t tb_unit_median_workspace_bytes(int32_t d);
+/* stage-by-stage form for sharded ensembles (same workspace): 0 local bucket histogram, 1 pick the bucket(s)
+ * of the global rank from the (all-reduced) histogram, 2 compact the local candidates, 3 exact select over the
+ * (merged) candidate lists.  tb_bucket_offsets: byte offsets {histogram u32[d][65536], selector records (24 B
+ * per column: b1, b2, rank_local i64, count u32, overflow i32), candidates f64[d][65536], multiplicities
+ * u32[d][65536]}.  unit_map != 0: keys in [0,1) bucketed by floor(v*65536); else by bits in [lo_value, hi_value]. */
+int tb_bucket_offsets(int32_t d, int64_t* out4);
+int tb_bucket_stage(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
+                    int64_t rank_lo, int32_t same, double lo_value, double hi_value, int32_t unit_map,
+                    int32_t stage, void* workspace, double* out, int32_t* overflow, tb_stream_t stream);
 int tb_unit_median_pair(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
                         int64_t rank_lo, void* workspace, double* out, int32_t* overflow,
                         tb_stream_t stream);

@@ -1087,6 +1087,57 @@ static int bucket_pair_launch(const double* u, const int64_t* rows, const int32_
   return e == cudaSuccess ? TB_OK : (int)e;
 }
 
+// The same pipeline stage by stage for sharded ensembles: the callers all-reduce the histogram after stage 0
+// and merge the ranks' candidate lists after stage 2 (tempest_b200/sharded.py).
+int tb_bucket_offsets(int32_t d, int64_t* out4) {
+  if (d <= 0 || !out4) return TB_ERR_ARG;
+  size_t off = 0;
+  out4[0] = (int64_t)off;  off += (sizeof(unsigned int) * (size_t)d * kMedBuckets + 255) / 256 * 256;   // hist u32[d][65536]
+  out4[1] = (int64_t)off;  off += (sizeof(MedSel) * (size_t)d + 255) / 256 * 256;                       // MedSel[d] (24 B each)
+  out4[2] = (int64_t)off;  off += sizeof(double) * (size_t)d * kMedCap;                                 // candidates f64[d][65536]
+  out4[3] = (int64_t)off;                                                                               // multiplicities u32[d][65536]
+  return TB_OK;
+}
+
+int tb_bucket_stage(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d, int64_t rank_lo,
+                    int32_t same, double lo_value, double hi_value, int32_t unit_map, int32_t stage, void* workspace,
+                    double* out, int32_t* overflow, tb_stream_t stream) {
+  if (d <= 0 || d > 4096 || n < 0 || rank_lo < 0 || !workspace || stage < 0 || stage > 3) return TB_ERR_ARG;
+  BucketMap bm;
+  if (unit_map) { bm.key_lo = 0ull; bm.shift = -1; }
+  else {
+    if (!(lo_value >= 0.0) || !(hi_value >= lo_value)) return TB_ERR_ARG;
+    unsigned long long klo, khi;
+    memcpy(&klo, &lo_value, 8);
+    memcpy(&khi, &hi_value, 8);
+    bm.key_lo = klo; bm.shift = 0;
+    while (((khi - klo) >> bm.shift) > 65535ull) ++bm.shift;
+  }
+  int64_t off[4];
+  tb_bucket_offsets(d, off);
+  char* p = (char*)workspace;
+  unsigned int* hist = (unsigned int*)(p + off[0]);
+  MedSel* sel = (MedSel*)(p + off[1]);
+  double* cval = (double*)(p + off[2]);
+  unsigned int* cmul = (unsigned int*)(p + off[3]);
+  cudaStream_t st = as_stream(stream);
+  const int grid = stream_grid((n > 0 ? n : 1) * d, kBlock * 4, 8);
+  if (stage == 0) {
+    cudaMemsetAsync(hist, 0, sizeof(unsigned int) * (size_t)d * kMedBuckets, st);
+    if (n > 0) { if (!u) return TB_ERR_ARG; med_hist_kernel<<<grid, kBlock, 0, st>>>(u, rows, mult, n, d, hist, bm); }
+  } else if (stage == 1) {
+    med_pick_kernel<<<d, 1024, 0, st>>>(hist, rank_lo, sel);
+  } else if (stage == 2) {
+    if (n > 0) { if (!u) return TB_ERR_ARG; med_compact_kernel<<<grid, kBlock, 0, st>>>(u, rows, mult, n, d, sel, cval, cmul, bm); }
+  } else {
+    if (!out || !overflow) return TB_ERR_ARG;
+    cudaMemsetAsync(overflow, 0, sizeof(int32_t), st);
+    med_small_kernel<<<d, 1024, 0, st>>>(sel, cval, cmul, out, overflow, same);
+  }
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
 int tb_unit_median_pair(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
                         int64_t rank_lo, void* workspace, double* out, int32_t* overflow, tb_stream_t stream) {
   if (n <= 0 || d <= 0 || d > 4096 || rank_lo < 0 || !u || !workspace || !out || !overflow) return TB_ERR_ARG;

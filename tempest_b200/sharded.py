@@ -121,6 +121,66 @@ class ShardedKernels(Kernels):
             self.comm.allreduce_sum_(t)
         return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
 
+    def bucket_pair_sharded(self, base, rows, mult, n: int, d: int, rank_lo: int, same: bool, lo_value: float,
+                            hi_value: float, unit_map: bool, build: bool, out: torch.Tensor) -> bool:
+        """Order statistics (rank_lo, rank_lo + 1) of every column of the GLOBAL multiset with the bucket
+        method: local 65 536-bucket histograms are all-reduced, every rank picks the same bucket(s), compacts
+        its own candidates, and the (few hundred) candidates are merged on every rank before the exact
+        in-block select.  Two small collectives instead of one all-reduce per radix level.  Returns False when
+        a bucket holds more candidates than the in-block select takes (the caller falls back to g_select_pair)."""
+        lib = self.lib
+        st = stream_ptr()
+        G = self.comm.world
+        bws = self.ws.bytes(f"bucket_sh{d}", lib.tb_unit_median_workspace_bytes(d))
+        if not hasattr(self, "_bucket_off"):
+            self._bucket_off = {}
+        if d not in self._bucket_off:
+            off = np.zeros(4, dtype=np.int64)
+            _lib.check(lib.tb_bucket_offsets(d, off.ctypes.data), "tb_bucket_offsets")
+            self._bucket_off[d] = [int(v) for v in off]
+        o0, o1, o2, o3 = self._bucket_off[d]
+        cap = 65536
+        ovf = self.ws.i32("bucket_ovf", 1)
+
+        def stage(k, out_=None, ovf_=None):
+            _lib.check(lib.tb_bucket_stage(ptr(base), ptr(rows), ptr(mult), n, d, int(rank_lo), int(same), float(lo_value),
+                                           float(hi_value), int(unit_map), k, ptr(bws), ptr(out_), ptr(ovf_), st),
+                       "tb_bucket_stage")
+
+        if build:
+            stage(0)
+            self.comm.allreduce_sum_(bws[o0: o0 + 4 * d * cap].view(torch.int32))
+        stage(1)
+        stage(2)
+        sel = bws[o1: o1 + 24 * d].view(torch.int32).reshape(d, 6)
+        allc = self.comm.allgather(sel[:, 4:6].contiguous()).cpu().numpy()        # [G, d, (count, overflow)]
+        counts = allc[:, :, 0].astype(np.int64)
+        totals = counts.sum(axis=0)
+        if allc[:, :, 1].any() or (totals > cap).any():
+            return False
+        maxc = int(counts.max())
+        if maxc > 0:
+            cval = bws[o2: o2 + 8 * d * cap].view(F64).reshape(d, cap)
+            cmul = bws[o3: o3 + 4 * d * cap].view(torch.int32).reshape(d, cap)
+            gv = self.comm.allgather(cval[:, :maxc].contiguous()).reshape(-1)        # [G, d, maxc]
+            gm = self.comm.allgather(cmul[:, :maxc].contiguous()).reshape(-1)
+            src, dst = [], []
+            for c in range(d):
+                pos = 0
+                for r in range(G):
+                    k_ = int(counts[r, c])
+                    if k_:
+                        src.append((r * d + c) * maxc + np.arange(k_))
+                        dst.append(c * cap + pos + np.arange(k_))
+                        pos += k_
+            src_t = torch.as_tensor(np.concatenate(src)).to(self.device)
+            dst_t = torch.as_tensor(np.concatenate(dst)).to(self.device)
+            cval.reshape(-1)[dst_t] = gv[src_t]
+            cmul.reshape(-1)[dst_t] = gm[src_t]
+        sel[:, 4] = torch.as_tensor(totals.astype(np.int32)).to(self.device)
+        stage(3, out, ovf)
+        return int(ovf.item()) == 0
+
     def g_select(self, base, rows, stride, m, ncols, mult, ranks, nranks, out):
         """Distributed radix select: local histograms, all-reduced per level, replicated picks."""
         lib = self.lib

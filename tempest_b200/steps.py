@@ -409,6 +409,10 @@ class Kernels:
                            "tb_bucket_select_pair")
                 hist_built[0] = True
                 done = int(ovf.item()) == 0
+            elif self.sharded:
+                done = self.bucket_pair_sharded(vals if m > 0 else None, None, None, m, 1, lo - below, hi == lo, comp_lo,
+                                                w_max, False, not hist_built[0], sel)
+                hist_built[0] = True
             if not done:
                 self.g_select_pair(vals, None, 1, m, 1, None, lo - below, hi == lo, sel)
             a, b = sel.cpu().numpy()
@@ -735,6 +739,9 @@ class Trainer:
             _lib.check(lib.tb_unit_median_pair(ptr(ens.u), ptr(idx), ptr(counts), n_trim, d, m_total // 2 - 1,
                                                ptr(mws_), ptr(pair), ptr(ovf), st), "tb_unit_median_pair")
             done = int(ovf.item()) == 0
+        else:
+            done = k.bucket_pair_sharded(ens.u, idx if n_trim else None, counts if n_trim else None, n_trim, d,
+                                         m_total // 2 - 1, False, 0.0, 1.0, True, True, pair)
         if not done:
             k.g_select_pair(ens.u, idx, d, n_trim, d, counts, m_total // 2 - 1, False, pair)
         mean = torch.empty((1, d), dtype=F64, device=core.device)
