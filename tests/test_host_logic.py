@@ -103,3 +103,46 @@ def test_philox_known_answers():
     for ctr, key, want in kat:
         got = philox4x32(*ctr, *key)
         assert tuple(int(v) for v in got) == want
+
+
+def test_callable_bridge_decides_batched_vs_rowwise_prior_on_the_host():
+    """callables.py: a prior that is elementwise may be called on the whole batch, one that indexes
+    coordinates must be called row by row like the reference does (mcmc.py:157)."""
+    import torch
+
+    from tempest_b200.callables import CallableBridge
+    from tempest_b200.config import SamplerConfig
+    from tempest_b200.registry import Rosenbrock, UniformPrior
+
+    def elementwise(u):
+        return 20.0 * u - 10.0
+
+    def rowwise(u):
+        x = np.empty(4)
+        x[0], x[1], x[2], x[3] = u[0], 2 * u[1], 3 * u[2], 4 * u[3]
+        return x
+
+    def like(x, shift=0.0):
+        return -np.sum(np.atleast_2d(x) ** 2, axis=1) + shift
+
+    dev = torch.device("cpu")
+    b1 = CallableBridge(SamplerConfig(elementwise, like, 4, vectorize=True), dev)
+    assert b1.external and b1.prior_batched and not b1.like_registry
+    b2 = CallableBridge(SamplerConfig(rowwise, like, 4, vectorize=True), dev)
+    assert b2.external and not b2.prior_batched
+    b3 = CallableBridge(SamplerConfig(UniformPrior(-1, 1, 4), Rosenbrock(4), 4, vectorize=True), dev)
+    assert not b3.external and b3.prior_registry and b3.like_registry
+    u = torch.rand((5, 4), dtype=torch.float64)
+    x2 = b2.prior(u, None)
+    np.testing.assert_array_equal(x2.numpy(), u.numpy() * np.array([1.0, 2.0, 3.0, 4.0]))
+    np.testing.assert_array_equal(b1.like(b1.prior(u, None)).numpy(), like(elementwise(u.numpy())))
+    # vectorize=False: one sample per call (core.py:323-326)
+    seen = []
+
+    def one(x):
+        seen.append(x.shape)
+        return float(-np.sum(x * x))
+
+    b4 = CallableBridge(SamplerConfig(elementwise, one, 4, vectorize=False), dev)
+    out = b4.like(torch.ones((3, 4), dtype=torch.float64))
+    assert seen == [(4,), (4,), (4,)] and out.shape == (3,)
