@@ -146,3 +146,15 @@ def test_callable_bridge_decides_batched_vs_rowwise_prior_on_the_host():
     b4 = CallableBridge(SamplerConfig(elementwise, one, 4, vectorize=False), dev)
     out = b4.like(torch.ones((3, 4), dtype=torch.float64))
     assert seen == [(4,), (4,), (4,)] and out.shape == (3,)
+
+
+def test_vectorised_percentile_positions_equal_the_scalar_form():
+    from tempest_b200.steps import percentile_position, percentile_positions
+
+    grid = np.linspace(0, 99, 1000)
+    for n in (1, 2, 5, 20, 4097, 123457, 37748736):
+        lo, hi, g = percentile_positions(n, grid)
+        ref = [percentile_position(n, float(p)) for p in grid]
+        np.testing.assert_array_equal(lo, [r[0] for r in ref])
+        np.testing.assert_array_equal(hi, [r[1] for r in ref])
+        np.testing.assert_array_equal(g, [r[2] for r in ref])
