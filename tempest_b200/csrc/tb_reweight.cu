@@ -100,7 +100,7 @@ __device__ __forceinline__ void probe1(Ess3& e, double& chk, double a) {
 }
 
 __device__ __forceinline__ void probe_slice(const double* __restrict__ logl, const double* __restrict__ C,
-                                            int64_t n, double beta, Ess3& e, double& bad) {
+                                            int64_t n, double beta, Ess3& e, double& bad, bool reverse = false) {
   // vectorised 2 x fp64 loads, 4 independent 16-byte loads in flight per thread
   const int64_t n2 = n >> 1;
   const double2* l2 = reinterpret_cast<const double2*>(logl);
@@ -108,16 +108,33 @@ __device__ __forceinline__ void probe_slice(const double* __restrict__ logl, con
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double chk = 0.0;
-  for (; i + stride < n2; i += 2 * stride) {
-    const double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
-    const double2 lb = __ldg(l2 + i + stride), cb = __ldg(c2 + i + stride);
-    probe4(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x), __dsub_rn(__dmul_rn(la.y, beta), ca.y),
-           __dsub_rn(__dmul_rn(lb.x, beta), cb.x), __dsub_rn(__dmul_rn(lb.y, beta), cb.y));
-  }
-  for (; i < n2; i += stride) {
-    const double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
-    probe1(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x));
-    probe1(e, chk, __dsub_rn(__dmul_rn(la.y, beta), ca.y));
+  if (!reverse) {
+    for (; i + stride < n2; i += 2 * stride) {
+      const double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
+      const double2 lb = __ldg(l2 + i + stride), cb = __ldg(c2 + i + stride);
+      probe4(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x), __dsub_rn(__dmul_rn(la.y, beta), ca.y),
+             __dsub_rn(__dmul_rn(lb.x, beta), cb.x), __dsub_rn(__dmul_rn(lb.y, beta), cb.y));
+    }
+    for (; i < n2; i += stride) {
+      const double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
+      probe1(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x));
+      probe1(e, chk, __dsub_rn(__dmul_rn(la.y, beta), ca.y));
+    }
+  } else if (i < n2) {
+    // same elements, last to first: the tail of the previous (forward) pass is still in L2
+    int64_t cnt = (n2 - 1 - i) / stride + 1;
+    int64_t j = i + (cnt - 1) * stride;
+    for (; cnt >= 2; cnt -= 2, j -= 2 * stride) {
+      const double2 la = __ldg(l2 + j), ca = __ldg(c2 + j);
+      const double2 lb = __ldg(l2 + j - stride), cb = __ldg(c2 + j - stride);
+      probe4(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x), __dsub_rn(__dmul_rn(la.y, beta), ca.y),
+             __dsub_rn(__dmul_rn(lb.x, beta), cb.x), __dsub_rn(__dmul_rn(lb.y, beta), cb.y));
+    }
+    if (cnt == 1) {
+      const double2 la = __ldg(l2 + j), ca = __ldg(c2 + j);
+      probe1(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x));
+      probe1(e, chk, __dsub_rn(__dmul_rn(la.y, beta), ca.y));
+    }
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
     probe1(e, chk, __dsub_rn(__dmul_rn(logl[n - 1], beta), C[n - 1]));
@@ -209,7 +226,7 @@ next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, 
   for (;;) {
     Ess3 e; e.init();
     double bad = 0.0;
-    probe_slice(logl, C, n, beta, e, bad);
+    probe_slice(logl, C, n, beta, e, bad, (nprobe & 1) != 0);   // alternate direction: reuse what the last pass left in L2
     block_merge_ess3(e, smem);
     bad = block_sum(bad, smem + 100);
     const int buf = nprobe & 1;
