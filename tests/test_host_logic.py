@@ -158,3 +158,23 @@ def test_vectorised_percentile_positions_equal_the_scalar_form():
         np.testing.assert_array_equal(lo, [r[0] for r in ref])
         np.testing.assert_array_equal(hi, [r[1] for r in ref])
         np.testing.assert_array_equal(g, [r[2] for r in ref])
+
+
+def test_plain_c_caller_compiles_and_links_against_the_abi(tmp_path):
+    """examples/next_beta_c_abi.c uses the library from C (no Python, no torch): it must compile as C
+    against include/tempest_b200.h and link against the shared object."""
+    import shutil
+    import subprocess
+
+    from tempest_b200 import _lib
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc) or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("nvcc or the built library is not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "next_beta_demo"
+    cmd = [nvcc, "-x", "c", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "next_beta_c_abi.c"),
+           "-L", os.path.dirname(_lib.LIB_PATH), "-ltempest_b200", "-lcudart", "-o", str(out)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert out.exists()
