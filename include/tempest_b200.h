@@ -388,6 +388,9 @@ int tb_split_by_label(const int32_t* labels, const int64_t* members, int64_t n, 
 /* testing hook: route every n_dim through the generic (runtime-d) step kernel instead of the
  * compile-time-d fast path (tape mode must give identical decisions on both) */
 int tb_set_mcmc_generic(int32_t on);
+/* n_dim without a compile-time instantiation (17..128): use the warp-cooperative runtime-d step kernel
+ * (tb_mcmc_wide.cu) instead of the per-thread one */
+int tb_set_mcmc_wide(int32_t on);
 
 /* out[i] = uniform [0,1) number i+offset of stream (seed, iteration, purpose): the draws the
  * host-driven resampling / training steps consume in Philox mode (purpose 4 / 5) */

@@ -12,6 +12,8 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TEMPEST_B200_LIB") or os.path.join(_HERE, "lib", "libtempest_b200.so")
 
+WIDE_DEFAULT = 1   # n_dim > 16: warp-cooperative runtime-d step kernel (tape parity at d = 50 / 100; 4.9x faster at d = 50)
+
 c_i32, c_i64, c_u32, c_u64, c_f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
 PTR = C.c_void_p
 SIZE = C.c_size_t
@@ -79,6 +81,7 @@ SIGNATURES = {
                                 PTR, PTR]),
     "tb_mcmc_accept": (c_i32, [c_i64, C.POINTER(TbMcmcParams), C.POINTER(TbTape), PTR, PTR, PTR, PTR, PTR, PTR, PTR,
                                PTR, PTR, PTR]),
+    "tb_set_mcmc_wide": (c_i32, [c_i32]),
     "tb_moments_workspace_bytes": (SIZE, [c_i32]),
     "tb_weighted_moments": (c_i32, [PTR, PTR, c_i64, c_i32, PTR, PTR, PTR, PTR]),
     "tb_mahalanobis_cv": (c_i32, [PTR, PTR, c_i64, c_i32, PTR, PTR, PTR, PTR, PTR]),
@@ -144,6 +147,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         per_call = KERNELS_PER_CALL.get(name)
         if per_call is not None:
             setattr(lib, name, _counted(fn, per_call))
+    # TEMPEST_B200_WIDE=0/1 selects the runtime-dimension step kernel for n_dim > 16 (see tb_mcmc_wide.cu)
+    lib.tb_set_mcmc_wide(int(os.environ.get("TEMPEST_B200_WIDE", str(WIDE_DEFAULT))))
     return lib
 
 

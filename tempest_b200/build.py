@@ -17,7 +17,7 @@ OBJDIR = os.path.join(HERE, "build" + os.environ.get("TB_OBJ_SUFFIX", ""))
 LIB = os.path.join(LIBDIR, os.environ.get("TB_LIB_NAME", "libtempest_b200.so"))   # TB_LIB_NAME / TB_NVCC_EXTRA: A/B builds
 SOURCES = ["tb_reweight.cu", "tb_resample.cu", "tb_moments.cu", "tb_linalg.cu", "tb_mcmc.cu", "tb_cluster.cu",
            "tb_mcmc_fast_a.cu", "tb_mcmc_fast_b.cu", "tb_mcmc_fast_c.cu", "tb_mcmc_fast_d.cu", "tb_mcmc_fast_e.cu",
-           "tb_mcmc_fast_f.cu"]
+           "tb_mcmc_fast_f.cu", "tb_mcmc_wide.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-warn-spills",

@@ -14,6 +14,7 @@
 #include "tb_mcmc_shared.cuh"
 
 static int tb_force_generic_mcmc = 0;
+static int tb_wide_mcmc = 0;     // n_dim without a compile-time instantiation: warp-cooperative kernel instead of the per-thread one
 
 namespace {
 using namespace tb;
@@ -322,6 +323,7 @@ bool params_ok(int64_t n, const tb_mcmc_params* p) {
 extern "C" {
 
 int tb_set_mcmc_generic(int32_t on) { tb_force_generic_mcmc = on ? 1 : 0; return TB_OK; }
+int tb_set_mcmc_wide(int32_t on) { tb_wide_mcmc = on ? 1 : 0; return TB_OK; }
 
 size_t tb_mcmc_workspace_bytes(int64_t n, int32_t n_modes) {
   const int64_t grid = (n + kMcmcBlock - 1) / kMcmcBlock;
@@ -419,6 +421,7 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
       default: break;
     }
   }
+  if (tb_wide_mcmc && !tb_force_generic_mcmc && p->like_id >= 0) return launch_wide(a, count, st);
   return launch_generic<0>(a, count, st);
 }
 

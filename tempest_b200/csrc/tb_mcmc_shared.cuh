@@ -206,6 +206,9 @@ __device__ inline void apply_step_update(const tb_mcmc_params& p, double* ctrl, 
 }
 
 
+// runtime-dimension step with the warp-cooperative redraw (tb_mcmc_wide.cu)
+int launch_wide(const StepArgs& a, int count, cudaStream_t st);
+
 // compile-time-dimension fast path, instantiated per dimension in tb_mcmc_fast_*.cu
 template <int D>
 int launch_fast(const StepArgs& a, int count, cudaStream_t st);
