@@ -280,7 +280,11 @@ size_t tb_mcmc_ctrl_doubles(int32_t n_modes);
  * q_k in [0,n) and the Student-t term -(D+nu)/2 log(1+q_k/nu) of the current state in [n,2n). */
 int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, const double* u,
                   double* qcur, void* workspace, double* ctrl, tb_stream_t stream);
-/* enqueue `count` Metropolis steps (each exits immediately once the stop rule has fired) */
+/* run up to `count` Metropolis steps in ONE persistent cooperative launch (registry likelihoods): the kernel
+ * stops by itself when the stop rule of mcmc.py:104-135,192-194 fires and leaves steps / done / sigma /
+ * acceptance in ctrl.  The workspace is private to the launch.  With p->xgpu the per-step totals of all
+ * ranks are exchanged over peer memory inside the kernel (every rank must launch with the same count);
+ * with defer_update it runs ONE step and leaves this rank's totals for an all-reduce + tb_mcmc_update. */
 int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const int32_t* assign,
                   double* u, double* logl, double* qcur, void* workspace, double* ctrl,
                   int32_t count, tb_stream_t stream);
@@ -391,11 +395,27 @@ int tb_set_mcmc_generic(int32_t on);
 /* n_dim without a compile-time instantiation (17..128): use the warp-cooperative runtime-d step kernel
  * (tb_mcmc_wide.cu) instead of the per-thread one */
 int tb_set_mcmc_wide(int32_t on);
+/* testing hook: 0 routes single-mode runs through the multi-mode instantiation of the fused step kernel
+ * (mode statistics in shared memory) instead of the constant-memory single-mode one (default 1) */
+int tb_set_mcmc_kone(int32_t on);
+/* testing hook: the three variates one Metropolis step of walker slot_offset+i consumes in Philox mode
+ * (mcmc.py:236,243,169), exactly as the step kernels generate them: gamma[n] standard-gamma variate of
+ * `shape`, z[n][d] the normals of redraw `attempt`, acc_u[n] the accept uniform (each nullable).
+ * family 0: fused kernels (tb_mcmc_steps), family 1: split step (tb_mcmc_propose / tb_mcmc_accept) */
+int tb_debug_variates(uint64_t seed, uint64_t iteration, int64_t slot_offset, int64_t n, int32_t step, int32_t d,
+                      double shape, int32_t attempt, int32_t family, double* gamma, double* z, double* acc_u,
+                      tb_stream_t stream);
 
 /* out[i] = uniform [0,1) number i+offset of stream (seed, iteration, purpose): the draws the
  * host-driven resampling / training steps consume in Philox mode (purpose 4 / 5) */
 int tb_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t purpose, int64_t offset,
                       int64_t n, double* out, tb_stream_t stream);
+
+/* measurement aid (bench.py): one launch of 8 * n_SM CTAs x 256 threads, each running eight independent
+ * register-resident fp64 FMA chains for `iters` iterations = tb_fp64_peak_flops(iters) flop; timed by the
+ * caller with CUDA events it gives the fp64 FMA peak the mutation kernel's roofline is quoted against */
+int64_t tb_fp64_peak_flops(int32_t iters);
+int tb_fp64_peak_run(int32_t iters, double* out, tb_stream_t stream);
 
 #ifdef __cplusplus
 }

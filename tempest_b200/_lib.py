@@ -82,6 +82,10 @@ SIGNATURES = {
     "tb_mcmc_accept": (c_i32, [c_i64, C.POINTER(TbMcmcParams), C.POINTER(TbTape), PTR, PTR, PTR, PTR, PTR, PTR, PTR,
                                PTR, PTR, PTR]),
     "tb_set_mcmc_wide": (c_i32, [c_i32]),
+    "tb_set_mcmc_kone": (c_i32, [c_i32]),
+    "tb_fp64_peak_flops": (c_i64, [c_i32]),
+    "tb_fp64_peak_run": (c_i32, [c_i32, PTR, PTR]),
+    "tb_debug_variates": (c_i32, [c_u64, c_u64, c_i64, c_i64, c_i32, c_i32, c_f64, c_i32, c_i32, PTR, PTR, PTR, PTR]),
     "tb_moments_workspace_bytes": (SIZE, [c_i32]),
     "tb_weighted_moments": (c_i32, [PTR, PTR, c_i64, c_i32, PTR, PTR, PTR, PTR]),
     "tb_mahalanobis_cv": (c_i32, [PTR, PTR, c_i64, c_i32, PTR, PTR, PTR, PTR, PTR]),
@@ -160,7 +164,7 @@ KERNELS_PER_CALL = {
     "tb_student_sigma": 1, "tb_median_pairs": 1, "tb_add_trace_reg": 1, "tb_normalize_inplace": 2,
     "tb_binade_hist": 1, "tb_subbin_hist": 1, "tb_masked_sums": 1, "tb_compact_ge": 3, "tb_select_ranks": 14, "tb_count_indices": 1,
     "tb_counted_moments": 2, "tb_prior_draw": 1, "tb_transform": 1, "tb_mcmc_begin": 2,
-    "tb_mcmc_steps": lambda args: int(args[9]), "tb_philox_uniform": 1, "tb_search_right_sharded": 1,
+    "tb_mcmc_steps": 1, "tb_debug_variates": 1, "tb_fp64_peak_run": 1, "tb_philox_uniform": 1, "tb_search_right_sharded": 1,
     "tb_scale_inplace": 1, "tb_select_stage": 1, "tb_select_pair": 11, "tb_unit_median_pair": 4, "tb_bucket_select_pair": 4, "tb_bucket_stage": 1, "tb_next_beta_x": 1, "tb_moments_partial": 2, "tb_mcmc_update": 1,
     "tb_search_right_guided": 2, "tb_search_right_sharded_guided": 2, "tb_mcmc_propose": 1, "tb_mcmc_accept": 1, "tb_kpp_prob": 1, "tb_kpp_pick": 1, "tb_gmm_init": lambda args: 4 + 2 * int(args[5]),
     "tb_gmm_em": lambda args: int(args[13]) * (3 + 2 * int(args[5])), "tb_gmm_bound": 1, "tb_gmm_prepare": 1,

@@ -303,6 +303,34 @@ class HierarchicalGaussianMixture:
         self._predict_block = block
         self._predict_d = d
 
+    # -- checkpointing: everything predict() needs (the fit itself is not resumable mid-way, nor does it need to be)
+    def state_dict(self) -> dict:
+        if not self._gmm_ready:
+            return {}
+        out = dict(clu_centres=np.array(self.cluster_centers_), clu_covs=np.array(self.cluster_covariances_),
+                   clu_weights=np.array(self.cluster_weights_), clu_d=np.array(self._predict_d))
+        if self._data_min is not None:
+            out.update(clu_min=np.array(self._data_min), clu_max=np.array(self._data_max))
+        return out
+
+    def load_state_dict(self, d: dict, device) -> None:
+        if "clu_centres" not in d:
+            return
+        self.cluster_centers_ = [np.array(c) for c in d["clu_centres"]]
+        self.cluster_covariances_ = [np.array(c) for c in d["clu_covs"]]
+        self.cluster_weights_ = np.array(d["clu_weights"])
+        self.n_clusters_ = len(self.cluster_centers_)
+        dim = int(d["clu_d"])
+        if "clu_min" in d:
+            self._data_min, self._data_max = np.array(d["clu_min"]), np.array(d["clu_max"])
+            self._lo = torch.as_tensor(self._data_min, dtype=F64).to(device)
+            self._hi = torch.as_tensor(self._data_max, dtype=F64).to(device)
+        else:
+            self._data_min = self._data_max = None
+            self._lo = self._hi = None
+        self._gmm_ready = self.n_clusters_ > 0
+        self._build_predictor(dim, device)
+
     def predict(self, X: torch.Tensor, rows: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
         """cluster.py:574-600: int32 device labels of ``X[rows]``."""
         if not self._gmm_ready:

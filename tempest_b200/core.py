@@ -48,6 +48,7 @@ class SamplerCore:
         self.state = DeviceState(config.n_dim, core=self)
         self.rng = PhiloxSource(config.random_state, self.device)
         self.trace: dict = {}
+        self.kernel_timing = None       # dict: bench.py collects (CUDA events, work) per launch of the two hot kernels
         self.n_mcmc_launches = 0
         self.n_total = 0
         self.logz_err = None
@@ -139,7 +140,7 @@ class SamplerCore:
         p.n_steps = cfg.n_steps
         p.n_max = cfg.n_max_steps
         p.beta = float(beta)
-        p.seed = self.rng.seed
+        p.seed = self.rng.key
         p.iteration = int(self.rng.iteration)
         p.slot_offset = self.slot_offset
         p.n_global = self.n_global
@@ -204,7 +205,7 @@ class SamplerCore:
         h = stats.cpu().numpy()
         logw = out.cpu().numpy()
         if not normalize:
-            logw = logw + h[4] + np.log(ens.n_total)   # undo the normalisation: logw_s = a_s + log N
+            logw = logw + h[4] + np.log(ens.n_total_global)   # undo the normalisation: logw_s = a_s + log N
         return logw, float(h[4])
 
     # -- the PS loop ----------------------------------------------------------------------------
@@ -226,6 +227,9 @@ class SamplerCore:
 
     def _initialize_fresh(self) -> None:                 # core.py:376-381 (history is NOT cleared)
         self.state.update_current({"iter": 0, "calls": 0, "beta": 0.0, "logz": 0.0})
+        # a run that starts on top of an existing history draws from a fresh Philox key (see PhiloxSource.key)
+        self.run_epoch = getattr(self, "run_epoch", 0) + 1 if self.ensemble.T > 0 else 0
+        self.rng.set_epoch(self.run_epoch)
 
     def _not_termination(self) -> bool:                  # core.py:360-374
         if self.ensemble.T == 0:
@@ -343,6 +347,11 @@ class SamplerCore:
             v = st.raw(key)
             if v is not None:
                 out["cur_" + key] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        if self.clusterer is not None:                       # the fitted hierarchy: predict() runs on iterations
+            out.update(self.clusterer.state_dict())          # with iter % cluster_every != 0 without a refit
+        if self.assign is not None:
+            out["core_assign"] = self.assign.detach().cpu().numpy()
+        out["run_epoch"] = np.array(getattr(self, "run_epoch", 0))
         tmp = path.with_suffix(path.suffix + ".temp")
         with open(tmp, "wb") as f:
             np.savez(f, **out)
@@ -357,6 +366,9 @@ class SamplerCore:
             raise ValueError(f"unknown state format {int(d['format'])}")
         if int(d["n_dim"]) != self.config.n_dim:
             raise ValueError(f"state has n_dim={int(d['n_dim'])}, sampler has n_dim={self.config.n_dim}")
+        if "n_particles" in d and int(d["n_particles"]) != self.config.n_particles:
+            raise ValueError(f"state has n_particles={int(d['n_particles'])}, sampler has "
+                             f"n_particles={self.config.n_particles}")
         ens = PersistentEnsemble(self.config.n_dim, self.device, world=self.comm.world)
         n = int(d["logl"].shape[0])
         if n:
@@ -391,9 +403,14 @@ class SamplerCore:
                 st.set_current(key, torch.as_tensor(d["cur_" + key]).to(self.device))
         if "cur_assignments" in d:
             st.set_current("assignments", d["cur_assignments"])
+        if self.clusterer is not None:
+            self.clusterer.load_state_dict(d, self.device)
+        self.assign = (torch.as_tensor(d["core_assign"]).to(self.device) if "core_assign" in d else None)
+        self.run_epoch = int(d["run_epoch"]) if "run_epoch" in d else 0
         st.set_current("x", None)
         self.n_total = int(d["n_total"])
         self.rng.seed = int(d["rng_seed"])                  # continue the same counter-based stream
+        self.rng.set_epoch(self.run_epoch)
         self._weights = None
 
     # -- results ----------------------------------------------------------------------------------

@@ -87,9 +87,35 @@ __global__ void add_trace_reg_kernel(double* __restrict__ cov, int d, double fac
   for (int i = threadIdx.x; i < d; i += blockDim.x) cov[i * d + i] += factor * tr;
 }
 
+// fp64 FMA peak probe for the roofline of the mutation kernel: eight independent register-resident DFMA chains
+// per thread, nothing else in the loop (the denominator MEASURED_PEAKS.json does not carry)
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(int iters, double seed, double* __restrict__ out) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
+  double a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 1.2345e300) out[0] = r;     // keeps the chains alive without a store on the timed path
+}
+
 }  // namespace
 
 extern "C" {
+
+int64_t tb_fp64_peak_flops(int32_t iters) {
+  return (int64_t)2 * 8 * (int64_t)iters * 256 * (int64_t)tb::sm_count() * 8;
+}
+
+int tb_fp64_peak_run(int32_t iters, double* out, tb_stream_t stream) {
+  if (iters <= 0 || !out) return TB_ERR_ARG;
+  fp64_peak_kernel<<<tb::sm_count() * 8, 256, 0, as_stream(stream)>>>(iters, 1.0, out);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
 
 int tb_chol_inv(double* a, int32_t d, int32_t batch, double* chol, double* inv, int32_t* info, double* norms3,
                 tb_stream_t stream) {

@@ -3,21 +3,47 @@
 //        tempest/mcmc.py:142-208 (step loop), :225-288 (tpCN), :301-323 (RWM),
 //        :104-135 (adaptive step count), :326-411 (boundaries)
 //
-// One thread per walker; one launch per Metropolis step.  A step proposes (Student-t scale,
-// Cholesky-preconditioned pCN or random-walk move, boundary map, redraw until inside the unit
-// cube), evaluates prior transform + likelihood in-kernel, accepts/rejects and leaves per-mode
-// partial sums; the last CTA folds them in a fixed order, adapts sigma_c and evaluates the stop
-// rule into a device-resident control block, so the next launch needs no host round trip (a
-// launch made after the stop rule fired returns immediately).
-// HBM traffic per step: the active set (u row, logl, q) is read once and written on accept;
-// proposals, normals and likelihood terms never leave registers.
+// Registry likelihoods: ONE persistent cooperative launch per mutation (tb_mcmc_fast.cuh for compile-time
+// n_dim <= 16, tb_mcmc_wide.cu for the rest; step loop, grid-wide + cross-GPU fold, sigma adaptation and
+// stop rule in tb_mcmc_shared.cuh).  A step proposes (Student-t scale, Cholesky-preconditioned pCN or
+// random-walk move, boundary map, redraw until inside the unit cube), evaluates prior transform +
+// likelihood in-kernel and accepts / rejects; proposals, normals and likelihood terms never leave
+// registers / shared memory, the active set (u row, logl, q) is read once per step and written on accept.
+// Caller-evaluated likelihoods use the per-launch runtime-dimension kernel below (split propose / accept step),
+// which is also the independent implementation the fused kernels are cross-checked against in the tests.
 #include "tb_mcmc_shared.cuh"
 
 static int tb_force_generic_mcmc = 0;
 static int tb_wide_mcmc = 0;     // n_dim without a compile-time instantiation: warp-cooperative kernel instead of the per-thread one
+namespace tb { int g_allow_kone = 1; }
 
 namespace {
 using namespace tb;
+
+// fold the per-CTA partials of the per-launch kernel, adapt sigma and evaluate the stop rule (mcmc.py:180-194, 104-135)
+__device__ inline void finish_step(const StepArgs& a, int K, int nparts) {
+  __shared__ double tot[kMaxModes + 3];
+  __shared__ double red[40];
+  const int W = K + 3;
+  McmcWs* ws = reinterpret_cast<McmcWs*>(a.ws);
+  // every thread sums a strided share of the rows, then a fixed-order CTA sum per column
+  for (int c = 0; c < W; ++c) {
+    double t = 0.0;
+    const bool mx = c == K + 2;       // error codes fold with max
+    for (int b = threadIdx.x; b < nparts; b += blockDim.x) {
+      const double r = __ldcg(ws->partial + (size_t)b * W + c);
+      t = mx ? fmax(t, r) : t + r;
+    }
+    t = mx ? block_max(t, red) : block_sum(t, red);
+    if (threadIdx.x == 0) tot[c] = t;
+  }
+  __syncthreads();
+  if (a.p.defer_update) {
+    for (int c = threadIdx.x; c < W; c += blockDim.x) a.ctrl[C_BASE + 3 * K + c] = tot[c];
+    return;
+  }
+  if (threadIdx.x == 0) apply_step_update(a.p, a.ctrl, tot, K);
+}
 
 // Runtime-dimension step kernel (any n_dim <= 128).
 // PHASE 0: whole step with the in-kernel registry likelihood.  PHASE 1: proposal only (written to
@@ -197,8 +223,9 @@ mcmc_step_kernel(StepArgs a) {
   const int W = K + 3;
   if (threadIdx.x == 0) { s_part[K] = nacc; s_part[K + 1] = npr; s_part[K + 2] = ner; }
   __syncthreads();
-  for (int e = threadIdx.x; e < W; e += blockDim.x) a.ws->partial[(size_t)blockIdx.x * W + e] = s_part[e];
-  if (last_block_arrives(&a.ws->ticket)) finish_step(a, K, gridDim.x);
+  McmcWs* ws = reinterpret_cast<McmcWs*>(a.ws);
+  for (int e = threadIdx.x; e < W; e += blockDim.x) ws->partial[(size_t)blockIdx.x * W + e] = s_part[e];
+  if (last_block_arrives(&ws->ticket)) finish_step(a, K, gridDim.x);
 }
 
 // q_k = (u_k - mu_c)^T Sigma_c^{-1} (u_k - mu_c) for the initial state; per-mode walker counts; sigma init
@@ -279,6 +306,59 @@ philox_uniform_kernel(uint64_t seed, uint64_t iteration, uint32_t purpose, int64
   }
 }
 
+// the three variates a production step consumes, as the step kernels generate them (family 0: fused kernels,
+// fp32 Box-Muller / Marsaglia-Tsang / spare-word accept uniform; family 1: per-launch kernel, all fp64)
+__global__ void __launch_bounds__(kBlock)
+debug_variates_kernel(uint64_t seed, uint64_t iteration, int64_t slot_offset, int64_t n, int step, int d, double shape,
+                      int attempt, int family, double* __restrict__ gamma, double* __restrict__ z,
+                      double* __restrict__ acc_u) {
+  const Philox rng(seed, iteration);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const uint64_t slot = (uint64_t)(slot_offset + k);
+    if (family == 0) {
+      uint32_t w = 0u; bool have = false;
+      const double g = gamma_mt(rng, slot, (uint32_t)step, shape, w, have);
+      if (gamma) gamma[k] = g;
+      if (acc_u) acc_u[k] = accept_uniform(rng, slot, (uint32_t)step, w, have);
+      if (z) {
+        const int ncall = (d + 3) / 4;
+        for (int cidx = 0; cidx < ncall; ++cidx) {
+          const uint4 r = rng.block((uint32_t)slot, (uint32_t)(slot >> 32), (uint32_t)step,
+                                    (RNG_NORMAL << 24) | (uint32_t)((attempt * ncall + cidx) & 0xffffff));
+          double nn[4];
+          bm_pair32(r.x, r.y, nn[0], nn[1]);
+          bm_pair32(r.z, r.w, nn[2], nn[3]);
+          for (int e = 0; e < 4; ++e) if (4 * cidx + e < d) z[k * d + 4 * cidx + e] = nn[e];
+        }
+      }
+    } else {
+      const double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+      double g = dd;
+      for (uint32_t trial = 0; trial < 64; ++trial) {
+        double n0, n1, u0, u1;
+        philox_n2(rng, slot, (uint32_t)step, 0x800000u | trial, n0, n1);
+        philox_u2(rng, slot, (uint32_t)step, RNG_GAMMA, trial, u0, u1, true);
+        const double v1 = 1.0 + cc * n0;
+        if (v1 <= 0.0) continue;
+        const double v = v1 * v1 * v1;
+        if (log(u0) < 0.5 * n0 * n0 + dd - dd * v + dd * log(v)) { g = dd * v; break; }
+      }
+      if (gamma) gamma[k] = g;
+      if (acc_u) { double a, b; philox_u2(rng, slot, (uint32_t)step, RNG_ACCEPT, 0, a, b, false); acc_u[k] = a; }
+      if (z) {
+        const int dp = d <= 2 ? 2 : d <= 4 ? 4 : d <= 6 ? 6 : d <= 8 ? 8 : d <= 10 ? 10 : d <= 16 ? 16 : d <= 32 ? 32 : d <= 64 ? 64 : 128;
+        for (int i = 0; i < d; i += 2) {
+          double z0, z1;
+          philox_n2(rng, slot, (uint32_t)step, (uint32_t)(attempt * ((dp + 1) / 2) + i / 2), z0, z1);
+          z[k * d + i] = z0;
+          if (i + 1 < d) z[k * d + i + 1] = z1;
+        }
+      }
+    }
+  }
+}
+
 template <int DP, int PHASE>
 int launch_steps(const StepArgs& a, int count, cudaStream_t st) {
   const int d = a.p.n_dim, K = a.p.n_modes;
@@ -324,14 +404,18 @@ extern "C" {
 
 int tb_set_mcmc_generic(int32_t on) { tb_force_generic_mcmc = on ? 1 : 0; return TB_OK; }
 int tb_set_mcmc_wide(int32_t on) { tb_wide_mcmc = on ? 1 : 0; return TB_OK; }
+int tb_set_mcmc_kone(int32_t on) { tb::g_allow_kone = on ? 1 : 0; return TB_OK; }
 
 size_t tb_mcmc_workspace_bytes(int64_t n, int32_t n_modes) {
   const int64_t grid = (n + kMcmcBlock - 1) / kMcmcBlock;
-  const size_t flat = 256 + sizeof(double) * (size_t)grid * (n_modes + 3);
-  const size_t tree = 256 + fold_workspace_bytes((int)((n + kFastBlock - 1) / kFastBlock), n_modes + 3);
-  return flat > tree ? flat : tree;
+  const size_t flat = 256 + sizeof(double) * (size_t)grid * (n_modes + 3);           // per-launch kernel
+  int64_t ctas = (n + 31) / 32;                                                         // persistent kernels (>= 1 warp per CTA)
+  const int64_t cap = (int64_t)tb::sm_count() * 32;
+  if (ctas > cap) ctas = cap;
+  const size_t pers = 256 + grid_sync_bytes((int)ctas, n_modes + 3);
+  return flat > pers ? flat : pers;
 }
-size_t tb_mcmc_ctrl_doubles(int32_t n_modes) { return C_BASE + 4 * (size_t)n_modes + 3; }
+size_t tb_mcmc_ctrl_doubles(int32_t n_modes) { return (size_t)ctrl_doubles(n_modes); }
 
 int tb_mcmc_update(const tb_mcmc_params* p, double* ctrl, tb_stream_t stream) {
   if (!p || !ctrl || p->n_modes <= 0 || p->n_modes > kMaxModes) return TB_ERR_ARG;
@@ -368,19 +452,28 @@ int tb_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t purpose, int64
   return TB_OK;
 }
 
+int tb_debug_variates(uint64_t seed, uint64_t iteration, int64_t slot_offset, int64_t n, int32_t step, int32_t d,
+                      double shape, int32_t attempt, int32_t family, double* gamma, double* z, double* acc_u,
+                      tb_stream_t stream) {
+  if (n <= 0 || d <= 0 || d > 128 || !(shape >= 1.0) || attempt < 0 || (family != 0 && family != 1)) return TB_ERR_ARG;
+  debug_variates_kernel<<<stream_grid(n, kBlock, 16), kBlock, 0, as_stream(stream)>>>(
+      seed, iteration, slot_offset, n, step, d, shape, attempt, family, gamma, z, acc_u);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
 int tb_mcmc_begin(int64_t n, const tb_mcmc_params* p, const int32_t* assign, const double* u, double* qcur,
                   void* workspace, double* ctrl, tb_stream_t stream) {
   if (!p || n <= 0 || p->n_dim <= 0 || p->n_dim > 128 || p->n_modes <= 0 || p->n_modes > kMaxModes || !u || !workspace ||
       !ctrl)
     return TB_ERR_ARG;
   cudaStream_t st = as_stream(stream);
-  // global ticket + the group tickets of the fast kernel's hierarchical fold
-  cudaError_t e = cudaMemsetAsync(workspace, 0, 16 + fold_ticket_bytes((int)((n + kFastBlock - 1) / kFastBlock)), st);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 16, st);       // ticket of the per-launch kernel
   if (e != cudaSuccess) return (int)e;
   mcmc_init_ctrl_kernel<<<1, 256, 0, st>>>(*p, ctrl);
   const int grid = (int)((n + kMcmcBlock - 1) / kMcmcBlock);
-  // the fast step kernel computes q itself on its first step
-  // (the generic and the split step kernels read it from qcur; like_id < 0 marks caller-evaluated likelihoods)
+  // the compile-time-dimension kernel computes q itself on its first step (the others read it from qcur;
+  // like_id < 0 marks caller-evaluated likelihoods)
   const bool need_q = p->sampler == TB_SAMPLE_TPCN &&
                       (tb_force_generic_mcmc || !has_fast_path(p->n_dim) || p->like_id < 0);
   mcmc_begin_kernel<<<grid, kMcmcBlock, 0, st>>>(n, *p, assign, u, need_q ? qcur : nullptr, ctrl);
@@ -393,15 +486,17 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
   if (!params_ok(n, p) || !u || !logl || !workspace || !ctrl || count < 0) return TB_ERR_ARG;
   if (p->sampler == TB_SAMPLE_TPCN && !qcur) return TB_ERR_ARG;
   if (p->rng_mode == TB_RNG_TAPE && !tape) return TB_ERR_ARG;
+  if (count == 0) return TB_OK;
   StepArgs a;
   a.n = n; a.p = *p;
   if (tape) a.tape = *tape; else { a.tape.gamma = nullptr; a.tape.acc_u = nullptr; a.tape.z = nullptr;
                                     a.tape.z_off = nullptr; a.tape.z_cnt = nullptr; a.tape.steps = 0; }
-  a.assign = assign; a.u = u; a.logl = logl; a.qcur = qcur; a.ws = (McmcWs*)workspace; a.ctrl = ctrl;
+  a.assign = assign; a.u = u; a.logl = logl; a.qcur = qcur; a.ws = workspace; a.ctrl = ctrl;
   a.ext_prop = nullptr; a.ext_logl = nullptr; a.ext_meta = nullptr;
+  a.max_steps = count;
   if (p->xgpu) {
     a.x = *p->xgpu;
-    if (a.x.world < 1 || a.x.world > kXMaxRanks || a.x.seq < 1 || p->n_modes + 3 > 15) return TB_ERR_ARG;
+    if (a.x.world < 1 || a.x.world > kXMaxRanks || a.x.seq < 1 || p->n_modes + 3 > kXMaxPayload) return TB_ERR_ARG;
     a.p.defer_update = 0;
   } else { a.x.rank = 0; a.x.world = 1; a.x.seq = 1; for (int i = 0; i < 8; ++i) a.x.peer[i] = nullptr; }
   a.p.xgpu = nullptr;
@@ -409,19 +504,19 @@ int tb_mcmc_steps(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, const
   const int d = p->n_dim;
   if (!tb_force_generic_mcmc) {
     switch (d) {   // compile-time dimension: fully unrolled, register-resident fast path
-      case 2: return launch_fast<2>(a, count, st);
-      case 3: return launch_fast<3>(a, count, st);
-      case 4: return launch_fast<4>(a, count, st);
-      case 5: return launch_fast<5>(a, count, st);
-      case 6: return launch_fast<6>(a, count, st);
-      case 8: return launch_fast<8>(a, count, st);
-      case 10: return launch_fast<10>(a, count, st);
-      case 12: return launch_fast<12>(a, count, st);
-      case 16: return launch_fast<16>(a, count, st);
+      case 2: return launch_fast<2>(a, st);
+      case 3: return launch_fast<3>(a, st);
+      case 4: return launch_fast<4>(a, st);
+      case 5: return launch_fast<5>(a, st);
+      case 6: return launch_fast<6>(a, st);
+      case 8: return launch_fast<8>(a, st);
+      case 10: return launch_fast<10>(a, st);
+      case 12: return launch_fast<12>(a, st);
+      case 16: return launch_fast<16>(a, st);
       default: break;
     }
   }
-  if (tb_wide_mcmc && !tb_force_generic_mcmc && p->like_id >= 0) return launch_wide(a, count, st);
+  if (tb_wide_mcmc && !tb_force_generic_mcmc && p->like_id >= 0) return launch_wide(a, st);
   return launch_generic<0>(a, count, st);
 }
 
@@ -438,7 +533,7 @@ static int split_args(StepArgs& a, int64_t n, const tb_mcmc_params* p, const tb_
   a.n = n; a.p = *p;
   if (tape) a.tape = *tape; else { a.tape.gamma = nullptr; a.tape.acc_u = nullptr; a.tape.z = nullptr;
                                     a.tape.z_off = nullptr; a.tape.z_cnt = nullptr; a.tape.steps = 0; }
-  a.assign = assign; a.u = u; a.logl = logl; a.qcur = qcur; a.ws = (McmcWs*)workspace; a.ctrl = ctrl;
+  a.assign = assign; a.u = u; a.logl = logl; a.qcur = qcur; a.ws = workspace; a.ctrl = ctrl; a.max_steps = 1;
   a.x.rank = 0; a.x.world = 1; a.x.seq = 1;
   for (int i = 0; i < 8; ++i) a.x.peer[i] = nullptr;
   return TB_OK;

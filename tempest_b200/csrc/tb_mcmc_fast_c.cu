@@ -2,6 +2,6 @@
 #include "tb_mcmc_fast.cuh"
 
 namespace tb {
-template int launch_fast<6>(const StepArgs& a, int count, cudaStream_t st);
-template int launch_fast<8>(const StepArgs& a, int count, cudaStream_t st);
+template int launch_fast<6>(const StepArgs& a, cudaStream_t st);
+template int launch_fast<8>(const StepArgs& a, cudaStream_t st);
 }  // namespace tb

@@ -2,5 +2,5 @@
 #include "tb_mcmc_fast.cuh"
 
 namespace tb {
-template int launch_fast<12>(const StepArgs& a, int count, cudaStream_t st);
+template int launch_fast<12>(const StepArgs& a, cudaStream_t st);
 }  // namespace tb

@@ -17,34 +17,41 @@ struct SmemCol {                     // column `lane` of a [d][32] shared array,
 };
 
 template <bool TPCN, bool TAPE>
-__global__ void __launch_bounds__(32)
-mcmc_step_wide(StepArgs a) {
-  if (a.ctrl[C_DONE] != 0.0) return;
-  extern __shared__ double sm[];
+struct WideBody {
+  static constexpr bool kSingleMode = false;
+  static constexpr int kWarps = 1;
+  __host__ __device__ static size_t cta_doubles(const tb_mcmc_params&) { return 0; }
+  // per-warp: proposal centre / winner [d][32], lane-private normals [d][32], lane-private proposal [d][32],
+  // proposal scale [32], attempts used + mode [32 + 32 ints]
+  __host__ __device__ static size_t warp_doubles(const tb_mcmc_params& p) { return 3 * 32 * (size_t)p.n_dim + 32 + 32; }
+  __device__ static void stage(const StepArgs&, double*) {}
+
+  __device__ static __forceinline__ void tile(const StepArgs& a, double*, double* s_warp, const double* s_ctrl,
+                                              int64_t tile, int step, TileAcc& acc, double* warp_alpha) {
   const int d = a.p.n_dim, K = a.p.n_modes;
-  double* s_x = sm;                  // [d][32] proposal centre, later the winning proposal
+  double* s_x = s_warp;              // [d][32] proposal centre, later the winning proposal
   double* s_z = s_x + d * 32;        // [d][32] lane-private normals; prior-transformed point in phase C
   double* s_p = s_z + d * 32;        // [d][32] lane-private proposal; centred proposal in phase C
-  __shared__ double s_cm[32];
-  __shared__ int s_used[32];
-  __shared__ int s_mode[32];
-  __shared__ double s_fold[kMaxModes + 3];
-  const int lane = threadIdx.x;
-  const int64_t k = (int64_t)blockIdx.x * 32 + lane;
+  double* s_cm = s_p + d * 32;
+  int* s_used = reinterpret_cast<int*>(s_cm + 32);
+  int* s_mode = s_used + 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t k = tile * 32 + lane;
   const bool valid = k < a.n;
-  const int step = (int)a.ctrl[C_STEPS];
   const Philox rng(a.p.seed, a.p.iteration);
-  const uint64_t slot0 = (uint64_t)(a.p.slot_offset + (int64_t)blockIdx.x * 32);
+  const uint64_t slot0 = (uint64_t)(a.p.slot_offset + tile * 32);
   const bool tape_over = TAPE && step >= a.tape.steps;
   const int ncall = (d + 3) / 4;
   int err = tape_over ? 1 : 0;
   int c = 0;
   double logl = 0.0, q = 0.0;
+  uint32_t acc_word = 0u;
+  bool have_acc_word = false;
   // ---- phase A: one walker per lane ----------------------------------------------------------
   if (valid) {
     c = a.assign ? a.assign[k] : 0;
     const double* mu = a.p.mode_mean + (size_t)c * d;
-    const double sig = a.ctrl[C_BASE + c], dof = __ldg(a.p.mode_dof + c);
+    const double sig = s_ctrl[C_BASE + c], dof = __ldg(a.p.mode_dof + c);
     const double* urow = a.u + k * d;
     logl = a.logl[k];
     double cm = sig, keep = 0.0;
@@ -52,23 +59,7 @@ mcmc_step_wide(StepArgs a) {
       q = a.qcur[k];                                   // tb_mcmc_begin computed it for the starting state
       double g;
       if (TAPE) g = tape_over ? 1.0 : a.tape.gamma[(int64_t)step * a.n + k];
-      else {   // Marsaglia-Tsang, shape = (d + nu)/2 >= 1
-        const double shape = 0.5 * ((double)d + dof);
-        const double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
-        g = dd;
-        for (uint32_t trial = 0; trial < 64; ++trial) {
-          const uint4 r = rng.block((uint32_t)(slot0 + lane), (uint32_t)((slot0 + lane) >> 32), (uint32_t)step,
-                                    (RNG_GAMMA << 24) | trial);
-          double n0, n1;
-          bm_pair32(r.x, r.y, n0, n1);
-          const double v1 = 1.0 + cc * n0;
-          if (v1 <= 0.0) continue;
-          const double v = v1 * v1 * v1;
-          const double uu = ((double)r.z + 0.5) * 2.3283064365386963e-10;
-          const double x2 = n0 * n0;
-          if (uu < 1.0 - 0.0331 * x2 * x2 || log(uu) < 0.5 * x2 + dd * (1.0 - v + log(v))) { g = dd * v; break; }
-        }
-      }
+      else g = gamma_mt(rng, slot0 + lane, (uint32_t)step, 0.5 * ((double)d + dof), acc_word, have_acc_word);
       const double gscale = 2.0 / (dof + q);
       cm = sig * sqrt(1.0 / (gscale * g));
       keep = sqrt(__dsub_rn(1.0, __dmul_rn(sig, sig)));
@@ -100,7 +91,7 @@ mcmc_step_wide(StepArgs a) {
       bool have = true;
       if (TAPE) {
         have = aidx < natt_sel;
-        const int64_t gk = (int64_t)blockIdx.x * 32 + wsel;
+        const int64_t gk = tile * 32 + wsel;
         const double* zt = a.tape.z + a.tape.z_off[(int64_t)step * a.n + gk] + (int64_t)(have ? aidx : 0) * d;
         for (int i = 0; i < d; ++i) s_z[i * 32 + lane] = zt[i];
       } else {
@@ -119,10 +110,11 @@ mcmc_step_wide(StepArgs a) {
         }
       }
       bool inside = have;
+      for (int j = 0; j < d; ++j) s_z[j * 32 + lane] *= cmul;     // L (c z), as the compile-time-dimension kernel
       for (int i = 0; i < d; ++i) {
         double lz = 0.0;
         const double* Li = L + (size_t)i * d;
-        for (int j = 0; j <= i; ++j) lz += (cmul * __ldg(Li + j)) * s_z[j * 32 + lane];
+        for (int j = 0; j <= i; ++j) lz += __ldg(Li + j) * s_z[j * 32 + lane];
         double v = s_x[i * 32 + wsel] + lz;
         const int kind = a.p.bc_kind ? a.p.bc_kind[i] : 0;
         v = bc_apply(v, kind);
@@ -154,9 +146,8 @@ mcmc_step_wide(StepArgs a) {
   __syncwarp();
   // ---- phase C: likelihood, Student-t ratio, accept -----------------------------------------------
   double alpha = 0.0;
-  int accepted = 0, nprop = 0;
   if (valid && s_used[lane] > 0) {
-    nprop = s_used[lane];
+    acc.nprop += s_used[lane];
     const double* mu = a.p.mode_mean + (size_t)c * d;
     const double* IV = a.p.mode_inv + (size_t)c * d * d;
     const double dof = __ldg(a.p.mode_dof + c);
@@ -185,51 +176,45 @@ mcmc_step_wide(StepArgs a) {
     alpha = al;
     double ur;
     if (TAPE) ur = a.tape.acc_u[(int64_t)step * a.n + k];
-    else {
-      const uint4 r = rng.block((uint32_t)(slot0 + lane), (uint32_t)((slot0 + lane) >> 32), (uint32_t)step, RNG_ACCEPT << 24);
-      ur = u53(r.x, r.y);
-    }
+    else ur = accept_uniform(rng, slot0 + lane, (uint32_t)step, acc_word, have_acc_word);
     if (ur < al) {
-      accepted = 1;
+      acc.accepted += 1;
       double* urow = a.u + k * d;
       for (int i = 0; i < d; ++i) urow[i] = s_x[i * 32 + lane];
       a.logl[k] = logl_new;
       if (TPCN) a.qcur[k] = q_new;
     }
   }
-  // ---- CTA partial row and the hierarchical fold ------------------------------------------------
-  const int W = K + 3;
-  double* part = fold_cta_partials(a.ws, gridDim.x, W) + (size_t)blockIdx.x * W;
+  acc.err = max(acc.err, err);
   for (int m = 0; m < K; ++m) {
     const double v = warp_sum((valid && c == m) ? alpha : 0.0);
-    if (lane == 0) part[m] = v;
+    if (lane == 0) warp_alpha[m] += v;
   }
-  {
-    const double na = warp_sum((double)accepted), npr = warp_sum((double)nprop), ne = warp_max((double)err);
-    if (lane == 0) { part[K] = na; part[K + 1] = npr; part[K + 2] = ne; }
+  __syncwarp();
   }
-  arrive_and_fold(a, K, s_fold);
+};
+
+template <bool TPCN, bool TAPE>
+__global__ void __launch_bounds__(32)
+mcmc_run_wide(const StepArgs a) {
+  extern __shared__ double dyn_smem[];
+  run_steps<WideBody<TPCN, TAPE>>(a, dyn_smem);
 }
 
 template <bool TPCN, bool TAPE>
-int launch_wide_variant(const StepArgs& a, int count, cudaStream_t st) {
-  const size_t smem = sizeof(double) * 3 * 32 * (size_t)a.p.n_dim;
-  if (smem > 40 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(mcmc_step_wide<TPCN, TAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
-  const int grid = (int)((a.n + 31) / 32);
-  for (int s = 0; s < count; ++s) mcmc_step_wide<TPCN, TAPE><<<grid, 32, smem, st>>>(a);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? TB_OK : (int)e;
+int launch_wide_variant(const StepArgs& a, cudaStream_t st) {
+  using Body = WideBody<TPCN, TAPE>;
+  const size_t smem = run_smem_bytes<Body>(a.p);
+  if (smem > 220 * 1024) return TB_ERR_UNSUPPORTED;
+  return launch_persistent(mcmc_run_wide<TPCN, TAPE>, Body::kWarps, a, smem, st);
 }
 
 }  // namespace
 
-int launch_wide(const StepArgs& a, int count, cudaStream_t st) {
+int launch_wide(const StepArgs& a, cudaStream_t st) {
   const bool tpcn = a.p.sampler == TB_SAMPLE_TPCN, tape = a.p.rng_mode == TB_RNG_TAPE;
-  if (tpcn) return tape ? launch_wide_variant<true, true>(a, count, st) : launch_wide_variant<true, false>(a, count, st);
-  return tape ? launch_wide_variant<false, true>(a, count, st) : launch_wide_variant<false, false>(a, count, st);
+  if (tpcn) return tape ? launch_wide_variant<true, true>(a, st) : launch_wide_variant<true, false>(a, st);
+  return tape ? launch_wide_variant<false, true>(a, st) : launch_wide_variant<false, false>(a, st);
 }
 
 }  // namespace tb

@@ -36,13 +36,12 @@ mixture_kernel(const double* __restrict__ logl, double* __restrict__ C, int64_t 
 }
 
 // ---- probe -------------------------------------------------------------------------
-struct ProbeWs {            // workspace layout (device)
+struct ProbeWs {            // workspace layout of probe_kernel (device)
   unsigned int ticket;      // last-block ticket
-  unsigned int barrier;     // grid barrier counter (next_beta)
-  unsigned int pad[2];
-  double partial[2][kMaxPartials][4];  // double-buffered {m, S1, S2, n_nonfinite}
-  double xmerged[2][4];                // sharded runs: cross-GPU merge of the ranks' triples (published by CTA 0)
+  unsigned int pad[3];
+  double partial[kMaxPartials][4];     // {m, S1, S2, n_nonfinite} per CTA
 };
+// next_beta_kernel uses a GridSync + rows[2][grid][4] (tb_xgpu.cuh) placed after this struct
 
 // exp(d) for d in (-40, 0]: Cody-Waite reduction by ln2, degree-13 Taylor polynomial on |r| <= ln2/2
 // (remainder < 5e-18), scaled by 2^k through the exponent field (k >= -58, no denormals).  <= 1 ulp of
@@ -141,20 +140,6 @@ __device__ __forceinline__ void probe_slice(const double* __restrict__ logl, con
   if (chk != chk) bad += 1.0;      // some a_s was NaN or +-inf (reported as a non-zero count)
 }
 
-// merge `nb` published partials in a fixed order; result identical in every caller
-__device__ __forceinline__ void merge_partials(const double (*part)[4], int nb, double* smem,
-                                               Ess3& e, double& bad) {
-  e.init();
-  bad = 0.0;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-    // L2 loads: the partials were published by other SMs
-    e.merge(__ldcg(&part[b][0]), __ldcg(&part[b][1]), __ldcg(&part[b][2]));
-    bad += __ldcg(&part[b][3]);
-  }
-  block_merge_ess3(e, smem);
-  bad = block_sum(bad, smem + 100);
-}
-
 __device__ __forceinline__ void write_probe_result(double* out, const Ess3& e, double bad) {
   out[0] = e.m; out[1] = e.s1; out[2] = e.s2;
   out[3] = (e.s1 * e.s1) / e.s2;      // ESS = 1 / sum (w/S1)^2
@@ -172,12 +157,13 @@ probe_kernel(const double* __restrict__ logl, const double* __restrict__ C, int6
   block_merge_ess3(e, smem);
   bad = block_sum(bad, smem + 100);
   if (threadIdx.x == 0) {
-    double* p = ws->partial[0][blockIdx.x];
+    double* p = ws->partial[blockIdx.x];
     p[0] = e.m; p[1] = e.s1; p[2] = e.s2; p[3] = bad;
   }
-  if (last_block_arrives(&ws->ticket)) {
-    merge_partials(ws->partial[0], gridDim.x, smem, e, bad);
-    if (threadIdx.x == 0) write_probe_result(out, e, bad);
+  if (last_block_arrives(&ws->ticket)) {      // the fold of the search kernel: (m, S1, S2) identical bit for bit
+    __shared__ double s_tot[4];
+    EssFold().rows(&ws->partial[0][0], gridDim.x, 4, s_tot);
+    if (threadIdx.x == 0) { e.m = s_tot[0]; e.s1 = s_tot[1]; e.s2 = s_tot[2]; write_probe_result(out, e, s_tot[3]); }
   }
 }
 
@@ -194,18 +180,39 @@ weights_kernel(const double* __restrict__ logl, const double* __restrict__ C, in
 }
 
 // ---- device-side next-beta search ---------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned int* counter) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int nb = gridDim.x;
-    unsigned int old = atomicAdd(counter, 1u);
-    unsigned int target = (old / nb + 1u) * nb;
-    while (*((volatile unsigned int*)counter) < target) { __nanosleep(20); }
-    __threadfence();
+// Row fold of grid_xreduce for (m, S1, S2, n_nonfinite) rows: Ess3 merges in a fixed order.
+struct EssFold {
+  // all threads of the CTA; thread t merges rows t, t + B, ... in ascending order, then the fixed-order CTA merge
+  __device__ void rows(const double* rows, int nb, int W, double* tot) const {
+    __shared__ double s_m[3 * 32 + 8];
+    __shared__ double s_b[40];
+    Ess3 e; e.init();
+    double bad = 0.0;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+      const double* r = rows + (size_t)b * W;
+      e.merge(__ldcg(r), __ldcg(r + 1), __ldcg(r + 2));
+      bad += __ldcg(r + 3);
+    }
+    block_merge_ess3(e, s_m);
+    bad = block_sum(bad, s_b);
+    if (threadIdx.x == 0) { tot[0] = e.m; tot[1] = e.s1; tot[2] = e.s2; tot[3] = bad; }
+    __syncthreads();
   }
-  __syncthreads();
-}
+  __device__ void ranks(const double* slots, int world, int W, double* tot) const {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+      Ess3 g; g.init();
+      double gb = 0.0;
+      for (int r = 0; r < world; ++r) {
+        const double* slot = slots + (size_t)r * kXSlotDoubles;
+        (void)ld_acquire_sys(reinterpret_cast<const unsigned long long*>(slot));
+        g.merge(ld_relaxed_sys(slot + 1), ld_relaxed_sys(slot + 2), ld_relaxed_sys(slot + 3));
+        gb += ld_relaxed_sys(slot + 4);
+      }
+      tot[0] = g.m; tot[1] = g.s1; tot[2] = g.s2; tot[3] = gb;
+    }
+  }
+};
 
 constexpr double kBetaTol = 1e-4, kBetaRtol = 1e-8, kEssTol = 0.01, kMetricAtol = 0.5;  // config.py:233-236
 constexpr int kMaxBisect = 200;                                                          // reweight.py:121
@@ -213,9 +220,10 @@ constexpr double kTiny = 2.2250738585072014e-308;
 
 __global__ void __launch_bounds__(kBlock, 5)
 next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n,
-                 double beta_prev, double target, int flags, ProbeWs* ws, double* __restrict__ result,
+                 double beta_prev, double target, int flags, GridSync* gs, double* __restrict__ result,
                  double* __restrict__ plog, int plog_cap, tb_xgpu xg) {
   __shared__ double smem[160];
+  __shared__ double s_part[4], s_tot[4];
   __shared__ double sh_beta;
   __shared__ int sh_done;
   // search state, replicated bit-identically in thread 0 of every CTA
@@ -229,31 +237,14 @@ next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, 
     probe_slice(logl, C, n, beta, e, bad, (nprobe & 1) != 0);   // alternate direction: reuse what the last pass left in L2
     block_merge_ess3(e, smem);
     bad = block_sum(bad, smem + 100);
-    const int buf = nprobe & 1;
+    if (threadIdx.x == 0) { s_part[0] = e.m; s_part[1] = e.s1; s_part[2] = e.s2; s_part[3] = bad; }
+    __syncthreads();
+    // one synchronisation point per probe: grid-wide fold, and on >1 GPU the merge of the ranks' triples over
+    // NVLink peer memory, fused (tb_xgpu.cuh); every CTA of every rank ends with the same (m, S1, S2)
+    const int rc = grid_xreduce(gs, xg, nprobe, 4, s_part, s_tot, EssFold());
     if (threadIdx.x == 0) {
-      double* p = ws->partial[buf][blockIdx.x];
-      p[0] = e.m; p[1] = e.s1; p[2] = e.s2; p[3] = bad;
-    }
-    grid_barrier(&ws->barrier);
-    merge_partials(ws->partial[buf], gridDim.x, smem, e, bad);
-    if (xg.world > 1) {
-      // fused collective: CTA 0 exchanges this rank's triple with every peer over NVLink, folds the
-      // ranks' triples in rank order and publishes the result to the other CTAs of this GPU
-      if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double mine[4] = {e.m, e.s1, e.s2, bad};
-        double all[kXMaxRanks * 4];
-        xgpu_allgather(xg, xg.seq + (unsigned long long)nprobe, mine, 4, all);
-        Ess3 g; g.init();
-        double gb = 0.0;
-        for (int r = 0; r < xg.world; ++r) { g.merge(all[4 * r], all[4 * r + 1], all[4 * r + 2]); gb += all[4 * r + 3]; }
-        ws->xmerged[buf][0] = g.m; ws->xmerged[buf][1] = g.s1; ws->xmerged[buf][2] = g.s2; ws->xmerged[buf][3] = gb;
-        __threadfence();
-      }
-      grid_barrier(&ws->barrier);
-      if (threadIdx.x == 0) {
-        e.m = __ldcg(&ws->xmerged[buf][0]); e.s1 = __ldcg(&ws->xmerged[buf][1]);
-        e.s2 = __ldcg(&ws->xmerged[buf][2]); bad = __ldcg(&ws->xmerged[buf][3]);
-      }
+      e.m = s_tot[0]; e.s1 = s_tot[1]; e.s2 = s_tot[2]; bad = s_tot[3];
+      if (rc) bad = NAN;               // a peer did not answer: stop the search, the host raises
     }
     if (threadIdx.x == 0) {
       double ess = (e.s1 * e.s1) / e.s2;
@@ -286,6 +277,7 @@ next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, 
         } else next = mid;
       }
       if (!done && phase == 3) next = (bmax + bmin) * 0.5;
+      if (bad != bad) done = 1;
       if (done && blockIdx.x == 0) {
         result[0] = beta; result[1] = e.m; result[2] = e.s1; result[3] = e.s2; result[4] = ess;
         result[5] = e.m + log(e.s1); result[6] = (double)nprobe; result[7] = (double)same;
@@ -329,8 +321,9 @@ int tb_mixture_append(const double* logl, double* C, int64_t n_old, int64_t n_ne
   return TB_OK;
 }
 
-size_t tb_probe_workspace_bytes(void) { return sizeof(ProbeWs); }
-size_t tb_next_beta_workspace_bytes(void) { return sizeof(ProbeWs); }
+// one allocation serves both kernels: [ProbeWs of probe_kernel | GridSync + rows of next_beta_kernel]
+size_t tb_probe_workspace_bytes(void) { return sizeof(ProbeWs) + grid_sync_bytes(kMaxPartials, 4); }
+size_t tb_next_beta_workspace_bytes(void) { return tb_probe_workspace_bytes(); }
 
 int tb_probe(const double* logl, const double* C, int64_t n, double beta, void* workspace, double* out6,
              tb_stream_t stream) {
@@ -389,8 +382,8 @@ int tb_next_beta_x(const double* logl, const double* C, int64_t n, double beta_p
   int64_t need = (n + kBlock * 4 - 1) / (kBlock * 4);
   int grid = (int)(need < max_coresident ? need : max_coresident);
   if (grid < 1) grid = 1;
-  ProbeWs* ws = (ProbeWs*)workspace;
-  cudaError_t e = cudaMemsetAsync(&ws->barrier, 0, sizeof(unsigned int), as_stream(stream));
+  GridSync* ws = reinterpret_cast<GridSync*>(reinterpret_cast<char*>(workspace) + sizeof(ProbeWs));
+  cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(GridSync), as_stream(stream));
   if (e != cudaSuccess) return (int)e;
   void* args[] = {(void*)&logl, (void*)&C, (void*)&n, (void*)&beta_prev, (void*)&ess_target, (void*)&flags,
                   (void*)&ws, (void*)&result, (void*)&probe_log, (void*)&probe_log_cap, (void*)&xg};

@@ -34,14 +34,25 @@ class PhiloxSource:
         self.seed = int(seed) if seed is not None else secrets.randbits(62)
         self.device = device
         self.iteration = 0
+        self.epoch = 0
         self.lib = _lib.load()
+
+    @property
+    def key(self) -> int:
+        """Philox key material: the seed, advanced per run epoch.  A second run() on the same Sampler continues on top
+        of the stored history with iter reset to 0 (core.py:376-381); keyed by (seed, iteration) alone it would redraw
+        the first run's particles bit for bit (the reference's MT19937 stream simply continues)."""
+        return (self.seed + self.epoch * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = int(epoch)
 
     def begin_iteration(self, iteration: int) -> None:
         self.iteration = int(iteration)
 
     def _uniform(self, purpose: int, n: int, offset: int = 0) -> torch.Tensor:
         out = torch.empty(n, dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.tb_philox_uniform(self.seed, self.iteration, purpose, offset, n, ptr(out),
+        _lib.check(self.lib.tb_philox_uniform(self.key, self.iteration, purpose, offset, n, ptr(out),
                                               stream_ptr()), "tb_philox_uniform")
         return out
 
@@ -73,8 +84,12 @@ class TapeSource:
         self.device = device
         self.cursor = -1
         self.seed = 0
+        self.key = 0
         self.iteration = 0
         self._keep = []
+
+    def set_epoch(self, epoch: int) -> None:
+        pass
 
     def begin_iteration(self, iteration: int) -> None:
         self.cursor += 1

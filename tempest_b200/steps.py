@@ -631,9 +631,17 @@ class Reweighter:
                 out = k.probe(ens, beta_prev)
                 return beta_prev, ess0, out
             flags = 1
+        timing = core.kernel_timing
+        if timing is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         res, plog = k.next_beta(ens, beta_prev, target, flags)
+        if timing is not None:
+            ev1.record()
         h = res.cpu().numpy()
         nprobe = int(h[6])
+        if timing is not None:           # (events, particle-probes of this launch)
+            timing.setdefault("next_beta", []).append((ev0, ev1, float(nprobe) * ens.n_total))
         hp = plog[: 2 * min(nprobe, 512)].cpu().numpy().reshape(-1, 2)
         self.probe_log.extend((float(b), float(e)) for b, e in hp)
         if k.sharded:
@@ -954,41 +962,45 @@ class Mutator:
         tape_ref = C.byref(tape) if tape is not None else None
         n_min = cfg.n_steps * d
         n_cap = cfg.n_max_steps * d
-        launched = 0
-        budget = min(n_min, n_cap)
-        fused = k.sharded and k.xgpu is not None and K + 3 <= 15
+        fused = k.sharded and k.xgpu is not None and K + 3 <= 71
         if core.bridge.external:
             h, launched = self._external_loop(params, tape, tape_ref, assign, u, logl, qcur, ws, ctrl, n_cap)
         elif k.sharded:
             k.comm.allreduce_sum_(ctrl[8 + K: 8 + 2 * K])          # walkers per mode: global counts
-        if fused:
-            params.xgpu = C.pointer(k.xgpu)                        # per-step all-reduce fused into the step kernel
-            params.defer_update = 0
-        elif k.sharded:
+        if k.sharded and not fused and not core.bridge.external:
             from .sharded import sharded_mcmc_loop
 
             h, launched = sharded_mcmc_loop(core, params, tape_ref, u, logl, qcur, ws, ctrl, min(n_min, n_cap),
                                             n_cap, self.CHUNK)
-        while (fused or not k.sharded) and not core.bridge.external:
-            if tape is not None:
-                budget = min(budget, tape.steps - launched)
-            if budget > 0:
-                _lib.check(lib.tb_mcmc_steps(n, C.byref(params), tape_ref, ptr(assign), ptr(u), ptr(logl), ptr(qcur),
-                                             ptr(ws), ptr(ctrl), int(budget), sp), "tb_mcmc_steps")
-                params.reserved = 1                    # same mode statistics for the rest of this mutation
-                launched += budget
+        elif not core.bridge.external:
+            # ONE persistent launch runs the whole mutation: the stop rule (mcmc.py:104-135, 192-194) is evaluated
+            # on the device every step, and on > 1 GPU the per-step totals travel over peer memory inside the kernel
+            if fused:
+                params.xgpu = C.pointer(k.xgpu)
+                params.defer_update = 0
+            budget = n_cap if tape is None else min(n_cap, tape.steps)
+            timing = core.kernel_timing
+            if timing is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            _lib.check(lib.tb_mcmc_steps(n, C.byref(params), tape_ref, ptr(assign), ptr(u), ptr(logl), ptr(qcur),
+                                         ptr(ws), ptr(ctrl), int(budget), sp), "tb_mcmc_steps")
+            if timing is not None:
+                ev1.record()
             h = ctrl.cpu().numpy()
-            if h[1] != 0.0 or launched >= n_cap:
-                break
-            if tape is not None and launched >= tape.steps:
+            if timing is not None:       # (events, walker-steps of this launch): bench.py's roofline of the dominant kernel
+                timing.setdefault("mcmc", []).append((ev0, ev1, float(h[0]) * n))
+            launched = 1
+            if fused:
+                k.consume_exchanges(int(h[0]))                     # one exchange per executed step
+            if h[1] == 0.0 and int(h[0]) < n_cap:
                 raise RuntimeError(
-                    f"tape holds {tape.steps} MCMC steps but the device stop rule has not fired after {launched}")
-            budget = min(self.CHUNK * (2 if fused else 1), n_cap - launched)   # steps are short when sharded
+                    f"tape holds {tape.steps if tape is not None else 0} MCMC steps but the device stop rule has "
+                    f"not fired after {int(h[0])}")
         core.n_mcmc_launches += launched
-        if fused and not core.bridge.external:
-            k.consume_exchanges(int(h[0]))                         # one exchange per executed step
         if h[4] != 0.0:
-            raise RuntimeError(f"MCMC kernel error flag {h[4]} (1: tape exhausted, 2: proposal never entered the cube)")
+            raise RuntimeError(f"MCMC kernel error code {int(h[4])} (1: tape exhausted, 2: proposal never entered the "
+                               "cube, 3: a peer GPU did not answer)")
         steps = int(h[0])
         sig = h[8:8 + K]
         sigma0 = 2.38 / math.sqrt(d)

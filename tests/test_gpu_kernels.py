@@ -360,6 +360,82 @@ def test_philox_uniforms_are_reproducible_and_uniform(env):
     assert torch.equal(a[1000:1100], b[:100])
 
 
+def _variates(env, n, d, shape, family, step=3, attempt=2, seed=987654321, iteration=9, slot_offset=0,
+              want=("gamma", "z", "acc")):
+    g = torch.empty(n, dtype=torch.float64, device=env.dev) if "gamma" in want else None
+    z = torch.empty((n, d), dtype=torch.float64, device=env.dev) if "z" in want else None
+    a = torch.empty(n, dtype=torch.float64, device=env.dev) if "acc" in want else None
+    env._lib.check(env.lib.tb_debug_variates(seed, iteration, slot_offset, n, step, d, float(shape), attempt, family,
+                                             env.ptr(g), env.ptr(z), env.ptr(a), env.sp()), "tb_debug_variates")
+    return g, z, a
+
+
+@pytest.mark.parametrize("shape", [0.5 * (10 + 1e6), 1.5])
+def test_production_variates_match_numpy_restatement(env, shape):
+    """The variates a Philox-mode Metropolis step consumes (the code tape mode replaces: tb::gamma_mt, normals_fixed,
+    accept_uniform) against oracle/philox.py, walker by walker.  The device evaluates the Box-Muller radius / angle
+    with MUFU log / sin / cos (abs. error ~2^-21), so equality is to 2e-5 absolute on |z| <= 6.76."""
+    from oracle import philox as ph
+
+    n, d, step, attempt, seed, it, off = 1 << 16, 10, 3, 2, 987654321, 9, 5_000_000_000
+    g, z, a = _variates(env, n, d, shape, 0, step, attempt, seed, it, off)
+    slots = off + np.arange(n, dtype=np.uint64)
+    zr = ph.step_normals(seed, it, slots, step, attempt, d)
+    np.testing.assert_allclose(z.cpu().numpy(), zr, rtol=0, atol=2e-5)
+    gr, ar, margin = ph.step_gamma(seed, it, slots, step, shape)
+    gd, ad = g.cpu().numpy(), a.cpu().numpy()
+    # a Marsaglia-Tsang comparison within 1e-5 of its threshold may resolve differently (fp32 normal inside it)
+    safe = margin > 1e-5
+    assert safe.mean() > 0.999
+    np.testing.assert_allclose(gd[safe], gr[safe], rtol=1e-8 if shape > 1e3 else 2e-4)
+    np.testing.assert_array_equal(ad[safe], ar[safe])             # the accept uniform is exact (one 32-bit word)
+    assert 0.0 < ad.min() and ad.max() < 1.0
+    # sharding invariance: the draws depend on the global slot only
+    g2, z2, a2 = _variates(env, 100, d, shape, 0, step, attempt, seed, it, off + 4000)
+    assert torch.equal(z2, z[4000:4100]) and torch.equal(g2, g[4000:4100]) and torch.equal(a2, a[4000:4100])
+
+
+def _ks_statistic(x: "torch.Tensor", cdf) -> float:
+    xs, _ = torch.sort(x.reshape(-1))
+    n = xs.numel()
+    f = cdf(xs)
+    i = torch.arange(1, n + 1, device=xs.device, dtype=torch.float64)
+    return float(torch.maximum((i / n - f).max(), (f - (i - 1) / n).max()))
+
+
+@pytest.mark.parametrize("family", [0, 1])
+def test_production_variates_distribution(env, family):
+    """Kolmogorov-Smirnov and moment checks of the production normals (10^8 draws for the fused kernels' fp32
+    Box-Muller), the Marsaglia-Tsang gamma (large shape through the series branch, small shape through the log
+    branch) and the accept uniform.  KS bound 1.95 / sqrt(n) is the 0.1 % critical value."""
+    from scipy import stats
+
+    n = (10_000_000 if family == 0 else 2_000_000)
+    d = 10
+    _, z, _ = _variates(env, n, d, 2.0, family, want=("z",))
+    m = n * d
+    assert _ks_statistic(z, lambda t: torch.special.ndtr(t)) < 1.95 / math.sqrt(m)
+    mean, var = float(z.mean()), float(z.var())
+    assert abs(mean) < 5.0 / math.sqrt(m) and abs(var - 1.0) < 5.0 * math.sqrt(2.0 / m)
+    assert abs(float((z ** 4).mean()) - 3.0) < 5.0 * math.sqrt(96.0 / m)
+    # independence across coordinates of a walker (blocks of four normals come from one Philox block)
+    zc = z[:1_000_000]
+    corr = torch.corrcoef(zc.T) - torch.eye(d, dtype=torch.float64, device=env.dev)
+    assert float(corr.abs().max()) < 6.0 / math.sqrt(zc.shape[0])
+    del z, zc
+    for shape in (0.5 * (10 + 1e6), 26.0, 1.0):
+        ng = 4_000_000
+        g, _, a = _variates(env, ng, d, shape, family, want=("gamma", "acc"))
+        gh, ah = g.cpu().numpy(), a.cpu().numpy()
+        ks = stats.kstest(gh, "gamma", args=(shape,)).statistic
+        assert ks < 1.95 / math.sqrt(ng), (shape, ks)
+        assert abs(gh.mean() / shape - 1.0) < 5.0 / math.sqrt(ng * shape)
+        assert abs(gh.var() / shape - 1.0) < 5.0 * math.sqrt(2.0 / ng) + 5.0 * math.sqrt(6.0 / (shape * ng))
+        assert stats.kstest(ah, "uniform").statistic < 1.95 / math.sqrt(ng)
+        # the accept uniform shares a Philox block with the accepted gamma trial: must be uncorrelated with it
+        assert abs(np.corrcoef(gh, ah)[0, 1]) < 5.0 / math.sqrt(ng)
+
+
 @pytest.mark.parametrize("n,d", [(1, 1), (2, 3), (4097, 1), (3001, 5), (200000, 10)])
 def test_select_pair_exact(env, n, d):
     rng = np.random.default_rng(n + d)

@@ -190,6 +190,60 @@ def test_generic_step_kernel_matches_oracle_on_tapes():
     np.testing.assert_allclose(s.state.get_history("logl"), np.array(o.hist["logl"]), rtol=1e-9, atol=1e-9)
 
 
+def test_multimode_instantiation_on_single_mode_runs_matches_oracle_on_tapes():
+    """Single-mode runs normally take the constant-memory instantiation <D, ., TAPE, KONE=1, LIKE> of the fused step
+    kernel -- the one bench.py times, run under the tapes by every test above.  This routes the same run through the
+    multi-mode instantiation (shared-memory operands, runtime likelihood switch): both must take the oracle's decisions."""
+    from tempest_b200 import _lib
+
+    lib = _lib.load()
+    lib.tb_set_mcmc_kone(0)
+    try:
+        o, s, _ = run_pair("rosen10_n64_tpcn_mult", max_iterations=12)
+    finally:
+        lib.tb_set_mcmc_kone(1)
+    np.testing.assert_array_equal(s.state.get_history("beta"), np.array(o.hist["beta"]))
+    np.testing.assert_array_equal(s.state.get_history("steps"), np.array(o.hist["steps"]))
+    np.testing.assert_allclose(s.state.get_history("u"), np.array(o.hist["u"]), rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(s.state.get_history("logl"), np.array(o.hist["logl"]), rtol=1e-9, atol=1e-9)
+    assert np.abs(s.state.get_history("u") - np.array(o.hist["u"])).max() < 1e-12
+
+
+@pytest.mark.parametrize("like", ["rosenbrock", "gaussian", "mixture", "shells"])
+def test_every_compile_time_likelihood_variant_matches_oracle_on_tapes(like):
+    """One short tape run per registry likelihood at n_dim = 10: each selects its own <10, tpCN, TAPE, KONE, LIKE>
+    instantiation (the production kernels differ from these only in the source of the three variates)."""
+    import tempest_b200 as tp
+    from oracle import ps_oracle as po
+    from tempest_b200.rng import TapeSource
+
+    d, n, iters = 10, 96, 9
+    prior = tp.UniformPrior(-6.0, 6.0, d)
+    if like == "rosenbrock":
+        L = tp.Rosenbrock(d)
+    elif like == "gaussian":
+        L = tp.GaussianLikelihood.ar1(d, 0.5)
+    elif like == "mixture":
+        rng = np.random.default_rng(3)
+        L = tp.IsotropicMixture(rng.uniform(-3, 3, (3, d)), [0.6, 0.9, 0.7], [0.2, 0.5, 0.3])
+    else:
+        L = tp.TwinShells(d)
+    o = po.OraclePS(prior, L, d, n_particles=n, stream=po.LegacyStream(31), record=True)
+    o.run(1 << 30, max_iterations=iters)
+    s = tp.Sampler(prior, L, d, n_particles=n, vectorize=True, clustering=False)
+    core = s._core
+    core.rng = TapeSource(o.tapes, core.device)
+    core._initialize_fresh()
+    for _ in range(iters):
+        core.execute_iteration(export=False)
+    st = s.state
+    np.testing.assert_array_equal(st.get_history("beta"), np.array(o.hist["beta"]))
+    np.testing.assert_array_equal(st.get_history("steps"), np.array(o.hist["steps"]))
+    np.testing.assert_allclose(st.get_history("logz"), np.array(o.hist["logz"]), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(st.get_history("logl"), np.array(o.hist["logl"]), rtol=1e-9, atol=1e-9)
+    assert np.abs(st.get_history("u") - np.array(o.hist["u"])).max() < 1e-12      # no accept / reject flip
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_sharded_run_matches_single_gpu():
     """Sharded over 2 ranks (NCCL) the run must reproduce the 1-GPU beta sequence, step counts and logZ."""
