@@ -93,6 +93,38 @@ int tb_next_beta(const double* logl, const double* C, int64_t n_total, double be
  * ---------------------------------------------------------------------------------- */
 size_t tb_cdf_workspace_bytes(int64_t n);
 int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_stream_t stream);
+/* The same over a SHARDED weight vector.  The global order is generation-major, rank-minor (the order of the
+ * single-GPU ensemble): this rank stores one contiguous segment per generation, seg_begin[n_gen + 1] (device)
+ * are their local start positions.  x: rank / world / call number seq (>= 1, +1 per call on every rank) and
+ * peer[r] = rank r's table memory (tb_cdf_x_table_bytes(ntg_cap) bytes of zero-initialised symmetric /
+ * peer-mapped memory) as addressed from this device; NULL or world 1 = one GPU, tables inside `workspace`.
+ * n_global: the global element count (sizes the launches; the same value on every rank).
+ * ntg_cap >= tb_cdf_tile_cap(n_global, n_gen * world), the same value on every rank and for every call that
+ * shares the table memory; workspace: tb_cdf_x_workspace_bytes(ntg_cap).
+ * Tile tables and the elements of the few tiles that cross a binade travel by peer stores between the
+ * stages; every rank launches the same call.  cdf receives this rank's part of numpy's cumsum of the global
+ * vector, bit for bit.  tb_cdf_status_ptr: device int32[16] {tiles, segments, runs, hard tiles, error code (0 ok,
+ * 3 peer timeout, 4/5 table capacity, 6 refuted hypothesis), ...}; tb_cdf_total_ptr: device double cdf[-1]. */
+typedef struct tb_cdf_x {
+  int32_t rank, world;
+  uint64_t seq;
+  void* peer[8];
+} tb_cdf_x;
+int64_t tb_cdf_tile_cap(int64_t n_global, int32_t n_segments);
+size_t tb_cdf_x_workspace_bytes(int64_t ntg_cap);
+size_t tb_cdf_x_table_bytes(int64_t ntg_cap);
+int32_t* tb_cdf_status_ptr(void* workspace);
+double* tb_cdf_total_ptr(void* workspace, int64_t ntg_cap);
+int tb_cdf_exact_x(const double* p, int64_t n_local, const int64_t* seg_begin, int32_t n_gen, int64_t n_global,
+                   int64_t ntg_cap, double* cdf, void* workspace, const tb_cdf_x* x, tb_stream_t stream);
+/* searches in the cdf of the last tb_cdf_exact_x call on `workspace` (same p / cdf / x arguments): two levels,
+ * exact tile-end values (identical on every rank) then the owner's local cdf.  systematic 0: m replicated
+ * uniforms `draws`, idx_k = numpy searchsorted(cdf / cdf[-1], u_k, 'right'); systematic 1: positions
+ * (u0 + k) / m, tools.py:217-226 (*overflow set when a position lies beyond the last weight).  idx_k = LOCAL
+ * index of the ancestor, or -1 when it is stored on another rank. */
+int tb_cdf_search_x(const double* p, int64_t n_local, double* cdf, void* workspace, int64_t ntg_cap,
+                    const tb_cdf_x* x, const double* draws, int64_t m, int32_t systematic, double u0,
+                    int64_t* idx, int32_t* overflow, tb_stream_t stream);
 int tb_cdf_sequential(const double* p, int64_t n, double* cdf, tb_stream_t stream);
 /* multinomial: idx_k = #{ j : cdf_j / cdf_{n-1} <= U_k }   (searchsorted side='right') */
 int tb_search_right(const double* cdf, int64_t n, const double* draws, int64_t m,

@@ -28,6 +28,10 @@ class TbXgpu(C.Structure):
     _fields_ = [("rank", c_i32), ("world", c_i32), ("seq", c_u64), ("peer", PTR * 8)]
 
 
+class TbCdfX(C.Structure):
+    _fields_ = [("rank", c_i32), ("world", c_i32), ("seq", c_u64), ("peer", PTR * 8)]
+
+
 class TbMcmcParams(C.Structure):
     _fields_ = [
         ("n_dim", c_i32), ("n_modes", c_i32), ("sampler", c_i32), ("rng_mode", c_i32),
@@ -55,6 +59,14 @@ SIGNATURES = {
     "tb_cdf_workspace_bytes": (SIZE, [c_i64]),
     "tb_cdf_exact": (c_i32, [PTR, c_i64, PTR, PTR, PTR]),
     "tb_cdf_sequential": (c_i32, [PTR, c_i64, PTR, PTR]),
+    "tb_cdf_tile_cap": (c_i64, [c_i64, c_i32]),
+    "tb_cdf_x_workspace_bytes": (SIZE, [c_i64]),
+    "tb_cdf_x_table_bytes": (SIZE, [c_i64]),
+    "tb_cdf_status_ptr": (PTR, [PTR]),
+    "tb_cdf_total_ptr": (PTR, [PTR, c_i64]),
+    "tb_cdf_exact_x": (c_i32, [PTR, c_i64, PTR, c_i32, c_i64, c_i64, PTR, PTR, C.POINTER(TbCdfX), PTR]),
+    "tb_cdf_search_x": (c_i32, [PTR, c_i64, PTR, PTR, c_i64, C.POINTER(TbCdfX), PTR, c_i64, c_i32, c_f64, PTR, PTR,
+                                PTR]),
     "tb_search_right": (c_i32, [PTR, c_i64, PTR, c_i64, PTR, PTR]),
     "tb_search_guide_bytes": (SIZE, [c_i32]),
     "tb_search_right_sharded_guided": (c_i32, [PTR, c_i64, PTR, PTR, PTR, c_i32, c_f64, PTR, c_i64, PTR, c_i32, PTR, PTR]),
@@ -159,7 +171,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
 # kernels each entry point enqueues (csrc/*.cu); used for the `gpu_launches` claim of bench.py
 KERNELS_PER_CALL = {
     "tb_mixture_build": 1, "tb_mixture_append": 1, "tb_probe": 1, "tb_weights": 1, "tb_log_weights": 1,
-    "tb_next_beta": 1, "tb_cdf_exact": 6, "tb_cdf_sequential": 1, "tb_search_right": 1, "tb_systematic": 1,
+    "tb_next_beta": 1, "tb_cdf_exact": 7, "tb_cdf_exact_x": 6, "tb_cdf_search_x": 1, "tb_cdf_sequential": 1, "tb_search_right": 1, "tb_systematic": 1,
     "tb_gather_rows": 1, "tb_weighted_moments": 2, "tb_mahalanobis_cv": 1, "tb_chol_inv": 1,
     "tb_student_sigma": 1, "tb_median_pairs": 1, "tb_add_trace_reg": 1, "tb_normalize_inplace": 2,
     "tb_binade_hist": 1, "tb_subbin_hist": 1, "tb_masked_sums": 1, "tb_compact_ge": 3, "tb_select_ranks": 14, "tb_count_indices": 1,

@@ -322,10 +322,17 @@ class SamplerCore:
     def save_sampler_state(self, path) -> None:
         from pathlib import Path
 
-        if self.comm.on:
-            raise NotImplementedError("checkpointing a sharded run is not built yet")
         path = Path(path)
         path.parent.mkdir(parents=True, exist_ok=True)
+        if self.comm.on:
+            # sharded run: every rank writes its own shard next to a manifest written by rank 0
+            if self.comm.rank == 0:
+                tmp = path.with_suffix(path.suffix + ".temp")
+                with open(tmp, "wb") as f:
+                    np.savez(f, format=np.array(self.STATE_FORMAT), world=np.array(self.comm.world),
+                             n_dim=np.array(self.config.n_dim), n_particles=np.array(self.config.n_particles))
+                tmp.replace(path)
+            path = path.with_suffix(path.suffix + f".rank{self.comm.rank}")
         ens, st = self.ensemble, self.state
         n = ens.n_total
         out = dict(
@@ -360,8 +367,17 @@ class SamplerCore:
     def load_sampler_state(self, path) -> None:
         from pathlib import Path
 
-        with np.load(Path(path)) as z:
+        path = Path(path)
+        if self.comm.on:
+            with np.load(path) as z:
+                man = {k: z[k] for k in z.files}
+            if "world" not in man or int(man["world"]) != self.comm.world:
+                raise ValueError(f"state was written by {int(man.get('world', 1))} rank(s), this job has {self.comm.world}")
+            path = path.with_suffix(path.suffix + f".rank{self.comm.rank}")
+        with np.load(path) as z:
             d = {k: z[k] for k in z.files}
+        if "world" in d and "u" not in d:
+            raise ValueError(f"state was written by a sharded run of {int(d['world'])} ranks; load it under torchrun")
         if int(d["format"]) != self.STATE_FORMAT:
             raise ValueError(f"unknown state format {int(d['format'])}")
         if int(d["n_dim"]) != self.config.n_dim:
@@ -428,11 +444,29 @@ class SamplerCore:
             k.weights(ens, 1.0, stats, lw, log=True)
             logw = lw.cpu().numpy()
         u, logl = ens.u[:n], ens.logl[:n]
+        idx = None
         if trim_importance_weights:                        # core.py:210-220
             idx, w = k.trim(w, n, ess=ess_trim, bins=bins_trim)
             u, logl = u[idx], logl[idx]
-        if resample and self.comm.on:
-            raise NotImplementedError("posterior(resample=True) is not sharded yet")
+        if resample and self.comm.on:                      # core.py:222-231 over the global (trimmed) weight vector
+            m_loc = int(w.numel())
+            m = k.g_int(m_loc)
+            bounds = self.generation_bounds()
+            seg_begin = torch.searchsorted(idx, bounds) if idx is not None else bounds
+            h = k.cdf_x(w, m_loc, seg_begin, m, "post_cdf")
+            pos = torch.empty(m, dtype=torch.int64, device=self.device)
+            k.search_x(h, None, m, pos, systematic=True, u0=self.rng.resample_u0())
+            own = torch.nonzero(pos >= 0).flatten()        # positions whose ancestor this rank stores
+            src = pos[own]
+            x = self.transform_to_x(u[src].contiguous())
+            allx, alll, allp = (self.comm.allgather_rows(t.contiguous()) for t in (x, logl[src], own))
+            order = torch.argsort(allp)                    # every rank returns the sample in position order
+            x, logl = allx[order], alll[order]
+            w = torch.full((m,), 1.0 / m, dtype=F64, device=self.device)
+            out = tuple(self._to_host(t) for t in (x, w, logl))
+            if logw is not None:
+                logw = self.comm.allgather_rows(torch.as_tensor(logw).to(self.device)).cpu().numpy()
+            return out + (logw,) if return_logw else out
         if resample:                                       # core.py:222-231
             m = int(w.numel())
             cdf = k.cdf(w, m, "post_cdf")

@@ -1,0 +1,924 @@
+// Bit-exact sequential cumulative sum in parallel, on one GPU or over a sharded weight vector (a8, a9;
+// App. C.1).   ref: numpy legacy RandomState.choice (cdf = cumsum(p); cdf /= cdf[-1]; searchsorted 'right'),
+//                   tempest/steps/resample.py:79-84, tempest/tools.py:178-228, tempest/modes.py:199-201
+//
+// numpy's cumsum is s_j = fl(s_{j-1} + p_j), strictly left to right; a parallel scan associates differently and
+// flips resampling indices.  While the running sum stays inside one binade [2^E, 2^{E+1}) its ulp q = 2^{E-52} is
+// constant, s = S q with S an integer in [2^52, 2^53), and for 0 <= p < 2^{E+1}
+//     fl(s + p) = (S + inc(p)) q,   inc(p) = floor(p/q) + [frac(p/q) > 1/2]      (exact ties: handled literally)
+// as long as the result stays below 2^{E+1}.  Integer addition IS associative, so inside a binade the sequential
+// cumsum is an int64 prefix sum; only the ~40 binade crossings of a real weight vector need the literal fp64 add.
+//
+// Pipeline (tiles of 1024 elements in GLOBAL order; G ranks, rank r stores one segment per generation, global order
+// = generation-major, rank-minor = the order of the single-GPU ensemble):
+//   plan     global tile table from the ranks' segment lengths                              (single CTA)
+//   K1       fp64 tile sums (approximate prefix, only used to GUESS each tile's binade)     (parallel, reads p)
+//   K2       scan of the tile sums, classification easy(E) / hard / zero                    (single CTA)
+//   K3       int64 tile totals of inc() under E; ties / oversized elements demote the tile  (parallel, reads p)
+//   K4       runs of equal E (int64 prefix inside a run); ONE CTA then carries the EXACT running sum through the
+//            runs (O(1) each, validated) and the hard tiles: 1024 threads resolve a hard tile in rounds of
+//            (inc under the current binade -> block scan -> first crossing / tie -> literal add of that element)
+//   K5       easy tiles: int64 in-tile scan -> cdf_j = (S_tile + incl_j) q                  (parallel, reads p, writes cdf)
+// Exactness never depends on a guess: every hypothesis is validated against the exact running sum.
+// Sharded: the tile tables (8 + 12 bytes per tile) and the elements of the hard tiles are pushed to every rank's
+// table memory over NVLink peer stores between the stages (one release flag per stage and rank, no host
+// involvement); every rank then runs the single-CTA stages redundantly on identical tables, so all ranks hold the
+// same exact tile-end values and the two-level search below returns numpy's global indices on any number of GPUs.
+#include "tb_common.cuh"
+#include "tb_xgpu.cuh"
+
+namespace {
+using namespace tb;
+
+constexpr int kTile = 1024;
+constexpr int kHard = INT32_MIN;       // tile class: resolved element by element by the walker
+constexpr int kZero = INT32_MIN + 1;   // tile class: leading all-zero tile (running sum still 0)
+constexpr int kMinE = -960;            // below this the power-of-two scale factors leave the normal range
+constexpr int kMaxSeg = 4096;          // layout segments (ranks x generations)
+constexpr int kMaxGen = kMaxSeg / kXMaxRanks;
+constexpr int kMaxHardX = 1024;        // hard tiles whose elements are exchanged in a sharded call
+constexpr int kPhases = 4;
+constexpr double kTinyNormal = 2.2250738585072014e-308;
+
+// ---- table memory (exchanged between ranks; one copy per call parity) -----------------------------------------
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+struct XLayout {
+  size_t flags, seglen, tsum, E, F, hard, total;
+};
+__host__ __device__ inline XLayout x_layout(int64_t ntg_cap) {
+  XLayout l;
+  size_t o = 0;
+  l.flags = o;  o += align_up(sizeof(unsigned long long) * kPhases * kXMaxRanks, 256);
+  l.seglen = o; o += align_up(sizeof(long long) * kXMaxRanks * kMaxGen, 256);
+  l.tsum = o;   o += align_up(sizeof(double) * ntg_cap, 256);
+  l.E = o;      o += align_up(sizeof(int) * ntg_cap, 256);
+  l.F = o;      o += align_up(sizeof(long long) * ntg_cap, 256);
+  l.hard = o;   o += align_up(sizeof(double) * (size_t)kMaxHardX * kTile, 256);
+  l.total = o;
+  return l;
+}
+
+struct Tables {            // resolved pointers into one rank's table memory (selected parity)
+  unsigned long long* flags;
+  long long* seglen;
+  double* tsum;
+  int* E;
+  long long* F;
+  double* hard;
+};
+__device__ __forceinline__ Tables tables_at(char* base, int64_t ntg_cap) {
+  const XLayout l = x_layout(ntg_cap);
+  Tables t;
+  t.flags = reinterpret_cast<unsigned long long*>(base + l.flags);
+  t.seglen = reinterpret_cast<long long*>(base + l.seglen);
+  t.tsum = reinterpret_cast<double*>(base + l.tsum);
+  t.E = reinterpret_cast<int*>(base + l.E);
+  t.F = reinterpret_cast<long long*>(base + l.F);
+  t.hard = reinterpret_cast<double*>(base + l.hard);
+  return t;
+}
+
+// ---- local scratch ---------------------------------------------------------------------------------------------
+struct Local {
+  int* status;            // [16]: 0 ntg, 1 nseg, 2 nruns, 3 nhard, 4 error, 5.. spare
+  unsigned int* tickets;  // [8]
+  int* seg_tile0;         // [kMaxSeg + 1]
+  int* seg_owner;         // [kMaxSeg]
+  long long* seg_len;     // [kMaxSeg]
+  long long* seg_local0;  // [kMaxSeg]
+  long long* G;           // [ntg_cap + 1] exclusive prefix of F over the easy tiles (global order)
+  int* run_of;            // [ntg_cap]
+  int* run_head;          // [ntg_cap + 1]
+  int* run_E;             // [ntg_cap]
+  double* run_s;          // [ntg_cap] exact running sum entering the run
+  long long* run_G0;      // [ntg_cap + 1] G at the run's first tile
+  int* hard_list;         // [ntg_cap] global tile ids of the hard tiles, in order
+  double* tile_end;       // [ntg_cap] exact cdf value of the tile's last element (level 1 of the sharded search)
+  long long* tile_off;    // [ntg_cap] local element offset of the tile, -1 when another rank stores it
+  int* tile_len;          // [ntg_cap] elements in the tile
+  double* total;          // [2]: cdf[-1], spare
+};
+__host__ __device__ inline size_t local_bytes(int64_t c) {
+  return 256 + 256 + align_up(4 * (kMaxSeg + 1), 256) + align_up(4 * kMaxSeg, 256) + 2 * align_up(8 * kMaxSeg, 256) +
+         align_up(8 * (c + 1), 256) + align_up(4 * c, 256) + align_up(4 * (c + 1), 256) + align_up(4 * c, 256) +
+         align_up(8 * c, 256) + align_up(4 * c, 256) + align_up(8 * c, 256) + align_up(8 * c, 256) + align_up(4 * c, 256) +
+         align_up(8 * (c + 1), 256) + 256;
+}
+__host__ __device__ inline Local local_at(char* p, int64_t c) {
+  Local w;
+  size_t o = 0;
+  w.status = reinterpret_cast<int*>(p + o);             o += 256;
+  w.tickets = reinterpret_cast<unsigned int*>(p + o);   o += 256;
+  w.seg_tile0 = reinterpret_cast<int*>(p + o);          o += align_up(4 * (kMaxSeg + 1), 256);
+  w.seg_owner = reinterpret_cast<int*>(p + o);          o += align_up(4 * kMaxSeg, 256);
+  w.seg_len = reinterpret_cast<long long*>(p + o);      o += align_up(8 * kMaxSeg, 256);
+  w.seg_local0 = reinterpret_cast<long long*>(p + o);   o += align_up(8 * kMaxSeg, 256);
+  w.G = reinterpret_cast<long long*>(p + o);            o += align_up(8 * (c + 1), 256);
+  w.run_of = reinterpret_cast<int*>(p + o);             o += align_up(4 * c, 256);
+  w.run_head = reinterpret_cast<int*>(p + o);           o += align_up(4 * (c + 1), 256);
+  w.run_E = reinterpret_cast<int*>(p + o);              o += align_up(4 * c, 256);
+  w.run_s = reinterpret_cast<double*>(p + o);           o += align_up(8 * c, 256);
+  w.hard_list = reinterpret_cast<int*>(p + o);          o += align_up(4 * c, 256);
+  w.tile_end = reinterpret_cast<double*>(p + o);        o += align_up(8 * c, 256);
+  w.tile_off = reinterpret_cast<long long*>(p + o);     o += align_up(8 * c, 256);
+  w.tile_len = reinterpret_cast<int*>(p + o);           o += align_up(4 * c, 256);
+  w.run_G0 = reinterpret_cast<long long*>(p + o);       o += align_up(8 * (c + 1), 256);
+  w.total = reinterpret_cast<double*>(p + o);
+  return w;
+}
+
+struct CdfArgs {
+  const double* p;        // this rank's weights (its segments, generation-major)
+  double* cdf;            // this rank's cdf values
+  int64_t n_local;
+  int64_t ntg_cap;
+  char* local;            // Local scratch
+  char* xbase[kXMaxRanks];// table memory of every rank as addressed from here (world == 1: [0] = own workspace)
+  int rank, world;
+  unsigned long long seq; // call number (>= 1): flags carry it
+};
+
+__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
+__device__ __forceinline__ int exponent_of(double x) { return (int)((__double_as_longlong(x) >> 52) & 0x7ff) - 1023; }
+__device__ __forceinline__ bool in_integer_regime(double s) {
+  if (!(s >= kTinyNormal) || !isfinite(s)) return false;
+  const int E = exponent_of(s);
+  return E >= kMinE && E <= 1000;
+}
+// inc(p) under binade E; -1 when the element cannot be handled by the integer rule (negative / NaN / at least a
+// quarter of 2^(E+1) / exact round-half tie).  round-to-nearest-even of p/q equals floor + [frac > 1/2] except at
+// ties, which are excluded, so the magic-number rounding (two DADDs, no fp64 -> int64 conversion) gives inc.
+__device__ __forceinline__ long long inc_of(double p, double up /* 2^(52-E) */, double top /* 2^(E+1) */) {
+  if (!(p >= 0.0) || !(p < 0.25 * top)) return -1;
+  const double sc = p * up;          // exact power-of-two scaling, < 2^51 (a denormal p may round: then sc << 1/2)
+  const double magic = 6755399441055744.0;                  // 2^52 + 2^51
+  const double t = sc + magic;       // round to nearest even integer
+  const double r = t - magic;
+  if (fabs(sc - r) == 0.5) return -1;
+  return __double_as_longlong(t) - __double_as_longlong(magic);
+}
+
+// ---- cross-rank stage flags ------------------------------------------------------------------------------------
+// called by ONE thread after this rank's stores of `phase` are complete and fenced (system scope)
+__device__ inline void signal_phase(const CdfArgs& a, int phase) {
+  for (int r = 0; r < a.world; ++r) {
+    Tables t = tables_at(a.xbase[r], a.ntg_cap);
+    st_release_sys(t.flags + phase * kXMaxRanks + a.rank, a.seq);
+  }
+}
+// called by all threads of a CTA: returns false on timeout
+__device__ inline bool wait_phase(const CdfArgs& a, int phase) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if ((int)threadIdx.x < a.world) {
+    Tables t = tables_at(a.xbase[a.rank], a.ntg_cap);
+    const unsigned long long* f = t.flags + phase * kXMaxRanks + threadIdx.x;
+    if (ld_acquire_sys(f) != a.seq) {
+      const unsigned long long t0 = global_ns();
+      while (ld_acquire_sys(f) != a.seq)
+        if (global_ns() - t0 > kXSpinBudgetNs) { s_ok = 0; break; }
+    }
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+// "all CTAs of this launch have finished their peer stores": last CTA signals the phase
+__device__ inline void arrive_and_signal(const CdfArgs& a, unsigned int* ticket, int phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *ticket = 0u;
+      __threadfence_system();
+      signal_phase(a, phase);
+    }
+  }
+}
+
+// segment of global tile g (last s with seg_tile0[s] <= g)
+__device__ __forceinline__ int seg_of_tile(const int* __restrict__ seg_tile0, int nseg, int g) {
+  int lo = 0, hi = nseg;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(seg_tile0 + mid) <= g) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// ---- plan ------------------------------------------------------------------------------------------------------
+// seg_begin[n_gen + 1]: local start positions of this rank's per-generation segments.
+__global__ void __launch_bounds__(256)
+cdf_plan_kernel(CdfArgs a, const int64_t* __restrict__ seg_begin, int n_gen) {
+  Local w = local_at(a.local, a.ntg_cap);
+  if (a.world > 1) {
+    for (int t = threadIdx.x; t < n_gen; t += blockDim.x) {
+      const long long len = seg_begin[t + 1] - seg_begin[t];
+      for (int r = 0; r < a.world; ++r) {
+        Tables tr = tables_at(a.xbase[r], a.ntg_cap);
+        tr.seglen[a.rank * kMaxGen + t] = len;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence_system(); signal_phase(a, 0); }
+    if (!wait_phase(a, 0)) { if (threadIdx.x == 0) w.status[4] = 3; return; }
+  }
+  Tables mine = tables_at(a.xbase[a.world > 1 ? a.rank : 0], a.ntg_cap);
+  const int G = a.world, nseg = n_gen * G;
+  if (threadIdx.x == 0) {
+    long long tiles = 0;
+    for (int t = 0; t < n_gen; ++t)
+      for (int r = 0; r < G; ++r) {
+        const int s = t * G + r;
+        const long long len = (G > 1) ? mine.seglen[r * kMaxGen + t] : (seg_begin[t + 1] - seg_begin[t]);
+        w.seg_len[s] = len;
+        w.seg_owner[s] = r;
+        w.seg_tile0[s] = (int)tiles;
+        tiles += (len + kTile - 1) / kTile;
+      }
+    w.seg_tile0[nseg] = (int)tiles;
+    for (int r = 0; r < G; ++r) {          // local offsets inside the owner's array
+      long long off = 0;
+      for (int t = 0; t < n_gen; ++t) { w.seg_local0[t * G + r] = off; off += w.seg_len[t * G + r]; }
+    }
+    w.status[0] = (int)tiles;
+    w.status[1] = nseg;
+    w.status[2] = 0; w.status[3] = 0;
+    w.status[4] = (tiles > a.ntg_cap) ? 4 : 0;
+  }
+}
+
+// ---- tile map: local offset / length of every global tile (parallel binary searches, once per call) -----------
+__global__ void __launch_bounds__(256)
+cdf_tile_map_kernel(CdfArgs a) {
+  Local w = local_at(a.local, a.ntg_cap);
+  const int ntg = w.status[0], nseg = w.status[1];
+  if (w.status[4] != 0) return;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ntg; g += gridDim.x * blockDim.x) {
+    const int s = seg_of_tile(w.seg_tile0, nseg, g);
+    const long long off = (long long)(g - w.seg_tile0[s]) * kTile;
+    w.tile_len[g] = (int)min((long long)kTile, w.seg_len[s] - off);
+    w.tile_off[g] = (w.seg_owner[s] == a.rank) ? w.seg_local0[s] + off : -1;
+  }
+}
+
+// The three streaming kernels give one WARP a tile: lane l reads elements 4 (32 k + l) .. + 3 for k = 0..7 (two
+// 16-byte loads per step, 1 KB contiguous per warp and step), eight warps per CTA, grid-stride over the tiles.
+constexpr int kTileWarps = 8;
+__device__ __forceinline__ void load4(const double* __restrict__ src, int len, int base, double (&v)[4]) {
+  if (base + 3 < len && ((reinterpret_cast<uintptr_t>(src + base) & 15) == 0)) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(src + base));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(src + base) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (base + e < len) ? __ldg(src + base + e) : 0.0;
+  }
+}
+
+// ---- K1: approximate tile sums ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kTileWarps)
+cdf_tile_sum_kernel(CdfArgs a) {
+  Local w = local_at(a.local, a.ntg_cap);
+  const int ntg = w.status[0];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (w.status[4] == 0) {
+    for (int g = blockIdx.x * kTileWarps + wid; g < ntg; g += gridDim.x * kTileWarps) {
+      const long long off = w.tile_off[g];
+      if (off < 0) continue;
+      const int len = w.tile_len[g];
+      const double* src = a.p + off;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        double v[4];
+        load4(src, len, 4 * (32 * k + lane), v);
+        acc += (v[0] + v[1]) + (v[2] + v[3]);
+      }
+      acc = warp_sum(acc);
+      if (lane < a.world) tables_at(a.xbase[lane], a.ntg_cap).tsum[g] = acc;
+    }
+  }
+  if (a.world > 1) arrive_and_signal(a, w.tickets + 0, 1);
+}
+
+// ---- warp scans -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long warp_incl_scan_ll(long long v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_incl_scan_d(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+// ---- K2: scan of the tile sums + classification (single CTA; warp w owns a contiguous range of tiles and walks it
+//      32 tiles at a time: coalesced loads, warp-level scans, one cross-warp combine) --------------------------------
+__global__ void __launch_bounds__(1024)
+cdf_classify_kernel(CdfArgs a) {
+  __shared__ double sh[40];
+  Local w = local_at(a.local, a.ntg_cap);
+  if (a.world > 1 && !wait_phase(a, 1)) { if (threadIdx.x == 0) w.status[4] = 3; return; }
+  if (w.status[4] != 0) return;
+  const int ntg = w.status[0];
+  Tables t = tables_at(a.xbase[a.world > 1 ? a.rank : 0], a.ntg_cap);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int per = ((ntg + nw - 1) / nw + 31) & ~31;         // tiles per warp, a multiple of 32
+  const int g0 = min(ntg, wid * per), g1 = min(ntg, g0 + per);
+  double mine = 0.0;
+  for (int g = g0 + lane; g < g1; g += 32) mine += t.tsum[g];
+  mine = warp_sum(mine);
+  if (lane == 0) sh[wid] = mine;
+  __syncthreads();
+  double run = 0.0;                                          // approximate running sum before tile g0
+  for (int i = 0; i < wid; ++i) run += sh[i];
+  for (int base = g0; base < g1; base += 32) {
+    const int g = base + lane;
+    const double v = (g < g1) ? t.tsum[g] : 0.0;
+    const double incl = warp_incl_scan_d(v, lane);
+    const double pe = run + incl, ps = pe - v;
+    if (g < g1) {
+      int E = kHard;
+      if (v == 0.0 && ps == 0.0) E = kZero;                 // leading zeros: the running sum is still exactly 0
+      else {
+        // relative guard 1e-7 >> worst-case deviation of any fp64 summation order for n < 2^29 non-negative terms
+        const double lo = ps * (1.0 - 1e-7), hi = pe * (1.0 + 1e-7);
+        if (ps > 0.0 && isfinite(hi) && lo >= kTinyNormal) {
+          const int ea = exponent_of(lo), eb = exponent_of(hi);
+          if (ea == eb && ea >= kMinE && ea <= 1000) E = ea;
+        }
+      }
+      t.E[g] = E;
+    }
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// ---- K3: integer tile totals -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kTileWarps)
+cdf_tile_inc_kernel(CdfArgs a) {
+  Local w = local_at(a.local, a.ntg_cap);
+  const int ntg = w.status[0];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (w.status[4] == 0) {
+    Tables me = tables_at(a.xbase[a.world > 1 ? a.rank : 0], a.ntg_cap);
+    for (int g = blockIdx.x * kTileWarps + wid; g < ntg; g += gridDim.x * kTileWarps) {
+      const long long off = w.tile_off[g];
+      if (off < 0) continue;
+      const int E = me.E[g];
+      long long tot = 0;
+      int bad = 0;
+      if (E != kHard && E != kZero) {
+        const int len = w.tile_len[g];
+        const double* src = a.p + off;
+        const double up = pow2(52 - E), top = pow2(E + 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int base = 4 * (32 * k + lane);
+          double v[4];
+          load4(src, len, base, v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const long long inc = (base + e < len) ? inc_of(v[e], up, top) : 0;
+            if (inc < 0) bad = 1; else tot += inc;
+          }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        tot = (long long)warp_sum_u64((unsigned long long)tot);
+      }
+      if (lane < a.world) {                // owners publish the final class of their tiles to every rank
+        Tables tr = tables_at(a.xbase[lane], a.ntg_cap);
+        tr.E[g] = bad ? kHard : E;
+        tr.F[g] = (bad || E == kHard || E == kZero) ? 0 : tot;
+      }
+    }
+  }
+  if (a.world > 1) arrive_and_signal(a, w.tickets + 1, 2);
+}
+
+// ---- K4a: runs of equal class, exclusive int64 prefix of F, list of hard tiles (single CTA of 1024 threads).
+//      Warp w owns a contiguous range of tiles and walks it 32 tiles at a time (coalesced loads, warp-level scans);
+//      one cross-warp combine ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+cdf_runs_kernel(CdfArgs a) {
+  __shared__ long long sh_f[33];
+  __shared__ long long sh_c[33];
+  Local w = local_at(a.local, a.ntg_cap);
+  if (a.world > 1 && !wait_phase(a, 2)) { if (threadIdx.x == 0) w.status[4] = 3; return; }
+  if (w.status[4] != 0) return;
+  const int ntg = w.status[0];
+  Tables t = tables_at(a.xbase[a.world > 1 ? a.rank : 0], a.ntg_cap);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int per = ((ntg + nw - 1) / nw + 31) & ~31;
+  const int g0 = min(ntg, wid * per), g1 = min(ntg, g0 + per);
+  auto classify = [&](int g, int& cls, bool& hard, bool& newrun, long long& f) {
+    cls = t.E[g];
+    const int prev = (g > 0) ? t.E[g - 1] : kHard;
+    hard = cls == kHard;
+    newrun = g == 0 || hard || prev == kHard || cls != prev;
+    f = (!hard && cls != kZero) ? t.F[g] : 0;
+  };
+  long long fsum = 0, cnt = 0;           // cnt packs (new runs << 32) | hard tiles
+  for (int g = g0 + lane; g < g1; g += 32) {
+    int cls; bool hard, newrun; long long f;
+    classify(g, cls, hard, newrun, f);
+    fsum += f;
+    cnt += ((long long)(newrun ? 1 : 0) << 32) | (long long)(hard ? 1 : 0);
+  }
+  fsum = (long long)warp_sum_u64((unsigned long long)fsum);
+  cnt = (long long)warp_sum_u64((unsigned long long)cnt);
+  if (lane == 0) { sh_f[wid] = fsum; sh_c[wid] = cnt; }
+  __syncthreads();
+  if (wid == 0) {
+    const long long xf = (lane < nw) ? sh_f[lane] : 0, xc = (lane < nw) ? sh_c[lane] : 0;
+    const long long fi = warp_incl_scan_ll(xf, lane), ci = warp_incl_scan_ll(xc, lane);
+    sh_f[lane] = fi - xf; sh_c[lane] = ci - xc;
+    if (lane == 31) { sh_f[32] = fi; sh_c[32] = ci; }
+  }
+  __syncthreads();
+  long long G = sh_f[wid];
+  int run = (int)(sh_c[wid] >> 32) - 1, hidx = (int)(sh_c[wid] & 0xffffffffLL);
+  for (int base = g0; base < g1; base += 32) {
+    const int g = base + lane;
+    int cls = kHard; bool hard = false, newrun = false; long long f = 0;
+    if (g < g1) classify(g, cls, hard, newrun, f);
+    const long long fi = warp_incl_scan_ll(f, lane);
+    const long long ci = warp_incl_scan_ll(((long long)(newrun ? 1 : 0) << 32) | (long long)(hard ? 1 : 0), lane);
+    if (g < g1) {
+      const int myrun = run + (int)(ci >> 32);
+      w.G[g] = G + fi - f;
+      w.run_of[g] = myrun;
+      if (newrun) { w.run_head[myrun] = g; w.run_E[myrun] = cls; w.run_G0[myrun] = G + fi - f; }
+      if (hard) w.hard_list[hidx + (int)(ci & 0xffffffffLL) - 1] = g;
+    }
+    G += __shfl_sync(0xffffffffu, fi, 31);
+    const long long ct = __shfl_sync(0xffffffffu, ci, 31);
+    run += (int)(ct >> 32);
+    hidx += (int)(ct & 0xffffffffLL);
+  }
+  if (threadIdx.x == 0) {
+    const int nr = (int)(sh_c[32] >> 32), nh = (int)(sh_c[32] & 0xffffffffLL);
+    w.G[ntg] = sh_f[32]; w.run_head[nr] = ntg; w.run_G0[nr] = sh_f[32]; w.status[2] = nr; w.status[3] = nh;
+    if (a.world > 1 && nh > kMaxHardX) w.status[4] = 5;
+  }
+}
+
+// ---- K4p: the elements of the hard tiles, gathered into the contiguous staging area of the table memory (of every
+//      rank when sharded) in hard-list order: the walker then reads them from a few L2-resident pages instead of
+//      paying DRAM + TLB latency per tile on its serial path ---------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cdf_push_hard_kernel(CdfArgs a) {
+  Local w = local_at(a.local, a.ntg_cap);
+  if (w.status[4] == 0) {
+    const int nhard = min(w.status[3], kMaxHardX);
+    for (int h = blockIdx.x; h < nhard; h += gridDim.x) {
+      const int g = w.hard_list[h];
+      const long long off = w.tile_off[g];
+      if (off < 0) continue;
+      const int len = w.tile_len[g];
+      for (int e = threadIdx.x; e < kTile; e += blockDim.x) {
+        const double v = (e < len) ? __ldg(a.p + off + e) : 0.0;
+        for (int r = 0; r < a.world; ++r) tables_at(a.xbase[r], a.ntg_cap).hard[(size_t)h * kTile + e] = v;
+      }
+    }
+  }
+  if (a.world > 1) arrive_and_signal(a, w.tickets + 2, 3);
+}
+
+// ---- K4b: the exact walk (single CTA of 256 threads: eight warps keep the rounds short, four elements per thread)
+constexpr int kWalkThreads = 256;
+constexpr int kPer = kTile / kWalkThreads;      // elements per thread
+constexpr int kHardStage = 1024;      // hard tiles whose descriptors are staged in shared memory at a time
+struct WalkShared {
+  double v[kTile];            // elements of the hard tile being resolved
+  union {
+    long long incl[2][kTile]; // inclusive inc prefix of the current round (buffers alternate between rounds)
+    double out[kTile];        // cdf values of the serial regime
+  };
+  long long woff[2][kWalkThreads / 32];       // warp totals of the current round
+  double s_bcast;
+  int i_bcast;
+  int c_bcast[2];
+  int rounds, serial;         // diagnostics of the last call
+  long long h_off[kHardStage];
+  int h_len[kHardStage];
+};
+
+// Resolve one tile literally, starting from the exact running sum s (replicated in all threads).
+// v[k]: element 4 j + k of thread j (0 beyond len); cdf_out: where this rank stores the tile's cdf values (null:
+// another rank's tile, only the running sum is carried).  A round: inc under the current binade (an element the
+// integer rule cannot take counts 2^53, so the prefix overflows exactly where it must stop) -> thread-local and
+// warp scans -> cross-warp offsets + the warp in which S + incl first reaches 2^53 -> that warp's ballot gives the
+// element c -> elements before c are final, element c is added literally (exact fp64 add), the next round starts
+// behind it.
+__device__ double walk_hard_tile(const double (&v)[kPer], int len, double s, double* cdf_out, WalkShared& S) {
+  constexpr int NW = kWalkThreads / 32;
+  const int j = threadIdx.x, lane = j & 31, wid = j >> 5, e0 = kPer * j;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) S.v[e0 + k] = v[k];
+  __syncthreads();
+  int start = 0, rnd = 0;
+  while (start < len) {
+    if (!in_integer_regime(s)) {
+      // running sum 0, subnormal, tiny, or non-finite: one thread adds literally until the integer rule applies
+      if (j == 0) {
+        double t = s;
+        int i = start;
+        while (i < len && !in_integer_regime(t)) { t = __dadd_rn(t, S.v[i]); S.out[i] = t; ++i; }
+        S.s_bcast = t; S.i_bcast = i; S.serial += i - start;
+      }
+      __syncthreads();
+      const int stop = S.i_bcast;
+      if (cdf_out) {
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) if (e0 + k >= start && e0 + k < stop) cdf_out[e0 + k] = S.out[e0 + k];
+      }
+      s = S.s_bcast;
+      start = stop;
+      __syncthreads();
+      continue;
+    }
+    if (j == 0) ++S.rounds;
+    const int E = exponent_of(s);
+    const double up = pow2(52 - E), top = pow2(E + 1), q = pow2(E - 52);
+    const long long S0 = __double2ll_rn(s * up);
+    const long long room = (1LL << 53) - S0;                    // the prefix is valid while incl < room
+    const int buf = rnd & 1;                                    // shared buffers alternate: no barrier at the round's end
+    long long* s_incl = S.incl[buf];
+    long long* s_woff = S.woff[buf];
+    long long l[kPer];
+    long long run = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int e = e0 + k;
+      long long inc = (e >= start && e < len) ? inc_of(v[k], up, top) : 0;
+      if (inc < 0) inc = 1LL << 53;
+      run += inc;
+      l[k] = run;                                               // inclusive inside the thread
+    }
+    const long long wi = warp_incl_scan_ll(run, lane);
+    if (lane == 31) s_woff[wid] = wi;
+    __syncthreads();                                            // (1) warp totals visible
+    long long before = wi - run;                                // prefix before this thread's first element
+    int cw = NW;                                                // warp in which the prefix stops (every thread finds it)
+    {
+      long long acc = 0;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        const long long tw = s_woff[i];
+        if (i < wid) before += tw;
+        acc += tw;
+        if (cw == NW && acc >= room) cw = i;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { l[k] += before; s_incl[e0 + k] = l[k]; }
+    if (wid == cw) {
+      const unsigned st = __ballot_sync(0xffffffffu, l[kPer - 1] >= room);
+      if (lane == __ffs(st) - 1) {
+        int k = 0;
+#pragma unroll
+        for (int kk = kPer - 1; kk >= 0; --kk) if (l[kk] >= room) k = kk;
+        S.c_bcast[buf] = e0 + k;
+      }
+    }
+    __syncthreads();                                            // (2) stop element and prefixes visible
+    const int c = (cw < NW) ? S.c_bcast[buf] : len;             // first crossing / tie / oversized element
+    if (cdf_out) {
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int e = e0 + k;
+        if (e >= start && e < len && e < c) cdf_out[e] = (double)(S0 + l[k]) * q;
+      }
+    }
+    if (c < len) {                                              // literal add of element c
+      const double s_prev = (c > start) ? (double)(S0 + s_incl[c - 1]) * q : s;
+      s = __dadd_rn(s_prev, S.v[c]);
+      if (cdf_out && j == c / kPer) cdf_out[c] = s;
+      start = c + 1;
+    } else {
+      if (len > start) s = (double)(S0 + s_incl[len - 1]) * q;
+      start = len;
+    }
+    ++rnd;
+  }
+  __syncthreads();
+  return s;
+}
+
+__global__ void __launch_bounds__(kWalkThreads)
+cdf_walk_kernel(CdfArgs a) {
+  extern __shared__ __align__(16) unsigned char walk_smem[];
+  WalkShared& S = *reinterpret_cast<WalkShared*>(walk_smem);
+  Local w = local_at(a.local, a.ntg_cap);
+  if (w.status[4] != 0) return;
+  Tables t = tables_at(a.xbase[a.world > 1 ? a.rank : 0], a.ntg_cap);
+  if (threadIdx.x == 0) { S.rounds = 0; S.serial = 0; }
+  const int nruns = w.status[2], nhard = w.status[3];
+  const int e0 = kPer * threadIdx.x;
+  const unsigned long long tb0 = global_ns();
+  if (a.world > 1) {
+    if (!wait_phase(a, 3)) { if (threadIdx.x == 0) w.status[4] = 3; return; }
+    if (nhard > kMaxHardX) return;       // status 5 was set by cdf_runs_kernel
+  }
+  // ---- the walk: run descriptors and hard-tile descriptors are staged through shared memory (no dependent global
+  //      loads per run); the elements of the next hard tile are fetched while the current one is resolved ---------
+  double s = 0.0;          // exact running sum (numpy: cdf_0 = p_0 = 0 + p_0)
+  constexpr int kChunk = 512;
+  __shared__ int c_head[kChunk + 1];
+  __shared__ int c_E[kChunk];
+  __shared__ long long c_G[kChunk + 1];
+  int hptr = 0;            // next entry of the hard list
+  int hbase = 0;           // first hard tile whose descriptor is staged
+  auto stage_hard = [&](int from) {      // all threads
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHardStage && from + i < nhard; i += blockDim.x) {
+      const int g = w.hard_list[from + i];
+      S.h_off[i] = w.tile_off[g];
+      S.h_len[i] = w.tile_len[g];
+    }
+    hbase = from;
+    __syncthreads();
+  };
+  auto fetch = [&](int h, double (&v)[kPer], int& len, long long& off) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) v[k] = 0.0;
+    len = 0; off = -1;
+    if (h >= nhard) return;
+    len = S.h_len[h - hbase];
+    off = S.h_off[h - hbase];
+    const double* src = (h < kMaxHardX) ? t.hard + (size_t)h * kTile : a.p + off;    // staged by cdf_push_hard_kernel
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) if (e0 + k < len) v[k] = src[e0 + k];
+  };
+  double v_next[kPer]; int len_next; long long off_next;
+  stage_hard(0);
+  fetch(0, v_next, len_next, off_next);
+  for (int r0 = 0; r0 < nruns; r0 += kChunk) {
+    const int cnt = min(kChunk, nruns - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i <= cnt; i += blockDim.x) {
+      c_head[i] = w.run_head[r0 + i];
+      c_G[i] = w.run_G0[r0 + i];
+      if (i < cnt) c_E[i] = w.run_E[r0 + i];
+    }
+    __syncthreads();
+    for (int i = 0; i < cnt; ++i) {
+      const int r = r0 + i;
+      const int head = c_head[i], next = c_head[i + 1], cls = c_E[i];
+      if (cls == kHard) {                // a hard tile is a run of its own, the next entry of the hard list
+        double v[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) v[k] = v_next[k];
+        const int len = len_next; const long long off = off_next;
+        ++hptr;
+        if (hptr < nhard && hptr - hbase >= kHardStage) stage_hard(hptr);
+        fetch(hptr, v_next, len_next, off_next);
+        s = walk_hard_tile(v, len, s, off >= 0 ? a.cdf + off : nullptr, S);
+        if (threadIdx.x == 0) w.tile_end[head] = s;
+        continue;
+      }
+      if (cls == kZero) { if (threadIdx.x == 0) w.run_s[r] = s; continue; }
+      const long long total = c_G[i + 1] - c_G[i];
+      bool valid = in_integer_regime(s) && exponent_of(s) == cls;
+      if (valid) {
+        const long long S0 = __double2ll_rn(s * pow2(52 - cls));
+        valid = (S0 + total) < (1LL << 53);
+        if (valid) {
+          if (threadIdx.x == 0) w.run_s[r] = s;
+          s = (double)(S0 + total) * pow2(cls - 52);
+        }
+      }
+      if (!valid) {      // hypothesis refuted (guarded by the 1e-7 margin; never observed): resolve the run literally
+        if (a.world > 1) { if (threadIdx.x == 0) w.status[4] = 6; return; }
+        for (int g = head + threadIdx.x; g < next; g += blockDim.x) t.E[g] = kHard;
+        __syncthreads();
+        for (int g = head; g < next; ++g) {
+          const int len = w.tile_len[g];
+          const long long off = w.tile_off[g];
+          double v[kPer];
+#pragma unroll
+          for (int k = 0; k < kPer; ++k) v[k] = (e0 + k < len) ? a.p[off + e0 + k] : 0.0;
+          s = walk_hard_tile(v, len, s, a.cdf + off, S);
+          if (threadIdx.x == 0) w.tile_end[g] = s;
+          __syncthreads();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    w.total[0] = s;
+    w.status[9] = (int)(global_ns() - tb0); w.status[11] = S.rounds; w.status[12] = S.serial;   // diagnostics
+
+  }
+}
+
+// ---- K4c: exact tile-end values of the easy tiles (level 1 of the sharded search; not needed on one GPU) --------
+__global__ void __launch_bounds__(256)
+cdf_tile_end_kernel(CdfArgs a) {
+  Local w = local_at(a.local, a.ntg_cap);
+  if (w.status[4] != 0) return;
+  const int ntg = w.status[0];
+  Tables t = tables_at(a.xbase[a.world > 1 ? a.rank : 0], a.ntg_cap);
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ntg; g += gridDim.x * blockDim.x) {
+    const int cls = t.E[g];
+    if (cls == kHard) continue;
+    const int r = w.run_of[g];
+    const double rs = w.run_s[r];
+    if (cls == kZero) { w.tile_end[g] = rs; continue; }
+    const long long S0 = __double2ll_rn(rs * pow2(52 - cls));
+    w.tile_end[g] = (double)(S0 + (w.G[g] - w.run_G0[r]) + t.F[g]) * pow2(cls - 52);
+  }
+}
+
+// ---- K5: finish easy tiles ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kTileWarps)
+cdf_emit_kernel(CdfArgs a) {
+  Local w = local_at(a.local, a.ntg_cap);
+  const int ntg = w.status[0];
+  if (w.status[4] != 0) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  Tables t = tables_at(a.xbase[a.world > 1 ? a.rank : 0], a.ntg_cap);
+  for (int g = blockIdx.x * kTileWarps + wid; g < ntg; g += gridDim.x * kTileWarps) {
+    const long long off = w.tile_off[g];
+    if (off < 0) continue;
+    const int E = t.E[g];
+    if (E == kHard) continue;
+    const int len = w.tile_len[g];
+    const double* src = a.p + off;
+    double* dst = a.cdf + off;
+    const int r = w.run_of[g];
+    const double rs = w.run_s[r];
+    if (E == kZero) {
+      for (int i = lane; i < len; i += 32) dst[i] = rs;
+      continue;
+    }
+    const double up = pow2(52 - E), top = pow2(E + 1), q = pow2(E - 52);
+    long long carry = __double2ll_rn(rs * up) + (w.G[g] - w.run_G0[r]);     // S before the tile's first element
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+#pragma unroll 2
+    for (int k = 0; k < 8; ++k) {
+      const int base = 4 * (32 * k + lane);
+      double v[4];
+      load4(src, len, base, v);
+      long long inc[4];
+      long long run = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        run += (base + e < len) ? inc_of(v[e], up, top) : 0;
+        inc[e] = run;                                      // inclusive within the lane's four elements
+      }
+      const long long incl = warp_incl_scan_ll(run, lane);
+      const long long before = carry + incl - run;
+      double o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (double)(before + inc[e]) * q;
+      if (base + 3 < len && aligned) {
+        reinterpret_cast<double2*>(dst + base)[0] = make_double2(o[0], o[1]);
+        reinterpret_cast<double2*>(dst + base)[1] = make_double2(o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (base + e < len) dst[base + e] = o[e];
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+
+// ---- two-level search in the global cdf (sharded runs) ----------------------------------------------------------
+// Level 1: first tile whose LAST cdf value exceeds the draw (tile_end[], identical on every rank); level 2: inside
+// that tile, in the owner's local cdf.  MODE 0: multinomial, count of cdf_j / cdf[-1] <= u (numpy searchsorted
+// 'right' after `cdf /= cdf[-1]`); MODE 1: systematic, first j with not (pos > cdf_j) (tools.py:219-226).
+// idx = LOCAL index of the ancestor, or -1 when it lives on another rank.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+cdf_search_x_kernel(CdfArgs a, const double* __restrict__ draws, int64_t m, double u0, int64_t* __restrict__ idx,
+                    int* __restrict__ overflow) {
+  Local w = local_at(a.local, a.ntg_cap);
+  const int ntg = w.status[0];
+  const double total = w.total[0];
+  const double* __restrict__ tend = w.tile_end;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride) {
+    const double u = MODE == 0 ? __ldg(draws + k) : __ddiv_rn(__dadd_rn(u0, (double)k), (double)m);
+    auto passes = [&](double c) -> bool { return MODE == 0 ? (__ddiv_rn(c, total) <= u) : (u > c); };
+    int lo = 0, hi = ntg;             // first tile whose last element does not pass
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (passes(__ldg(tend + mid))) lo = mid + 1; else hi = mid; }
+    if (lo >= ntg) { if (MODE == 1) *overflow = 1; idx[k] = -1; continue; }
+    const int g = lo;
+    const long long off = w.tile_off[g];
+    if (off < 0) { idx[k] = -1; continue; }
+    const int len = w.tile_len[g];
+    const double* c = a.cdf + off;
+    int l = 0, h = len - 1;           // the last element is known not to pass
+    while (l < h) { const int mid = (l + h) >> 1; if (passes(__ldg(c + mid))) l = mid + 1; else h = mid; }
+    idx[k] = off + l;
+  }
+}
+
+__global__ void cdf_set_bounds_kernel(int64_t* seg, int64_t n) { seg[0] = 0; seg[1] = n; }
+
+CdfArgs make_args(const double* p, int64_t n_local, double* cdf, void* workspace, int64_t ntg_cap, const tb_cdf_x* x) {
+  CdfArgs a;
+  a.p = p; a.cdf = cdf; a.n_local = n_local; a.ntg_cap = ntg_cap;
+  a.local = reinterpret_cast<char*>(workspace);
+  for (int r = 0; r < kXMaxRanks; ++r) a.xbase[r] = nullptr;
+  if (x && x->world > 1) {
+    a.rank = x->rank; a.world = x->world; a.seq = x->seq;
+    const size_t par = (x->seq & 1ull) ? x_layout(ntg_cap).total : 0;
+    for (int r = 0; r < x->world; ++r) a.xbase[r] = reinterpret_cast<char*>(x->peer[r]) + par;
+  } else {
+    a.rank = 0; a.world = 1; a.seq = 1;
+    a.xbase[0] = a.local + local_bytes(ntg_cap);
+  }
+  return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t tb_cdf_tile_cap(int64_t n_global, int32_t n_segments) {
+  return (n_global + kTile - 1) / kTile + (n_segments > 0 ? n_segments : 1);
+}
+size_t tb_cdf_x_workspace_bytes(int64_t ntg_cap) { return local_bytes(ntg_cap) + x_layout(ntg_cap).total + 256; }
+size_t tb_cdf_x_table_bytes(int64_t ntg_cap) { return 2 * x_layout(ntg_cap).total; }
+size_t tb_cdf_workspace_bytes(int64_t n) { return tb_cdf_x_workspace_bytes(tb_cdf_tile_cap(n, 1)); }
+
+// status of the last call on this workspace: {tiles, segments, runs, hard tiles, error, ...} (device ints)
+int32_t* tb_cdf_status_ptr(void* workspace) { return reinterpret_cast<int32_t*>(workspace); }
+double* tb_cdf_total_ptr(void* workspace, int64_t ntg_cap) { return local_at(reinterpret_cast<char*>(workspace), ntg_cap).total; }
+
+int tb_cdf_exact_x(const double* p, int64_t n_local, const int64_t* seg_begin, int32_t n_gen, int64_t n_global,
+                   int64_t ntg_cap, double* cdf, void* workspace, const tb_cdf_x* x, tb_stream_t stream) {
+  if (n_local < 0 || n_gen <= 0 || !seg_begin || !workspace || ntg_cap <= 0 || (n_local > 0 && (!p || !cdf))) return TB_ERR_ARG;
+  const int world = (x && x->world > 1) ? x->world : 1;
+  if (world > kXMaxRanks || n_gen * world > kMaxSeg || ntg_cap > 0x7ffffff0) return TB_ERR_UNSUPPORTED;
+  if (world > 1 && x->seq < 1) return TB_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  const CdfArgs a = make_args(p, n_local, cdf, workspace, ntg_cap, x);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 512, st);          // status + tickets
+  if (e != cudaSuccess) return (int)e;
+  // the tile kernels are launched over an upper bound of the global tile count (n_global: the same number on every
+  // rank); the exact count is only known on the device, surplus CTAs exit at once
+  int64_t grid = tb_cdf_tile_cap(n_global > 0 ? n_global : 1, n_gen * world);
+  if (grid > ntg_cap) grid = ntg_cap;
+  cdf_plan_kernel<<<1, 256, 0, st>>>(a, seg_begin, n_gen);
+  const int cap_ctas = sm_count() * 8;
+  int tgrid = (int)((grid + kTileWarps - 1) / kTileWarps);
+  if (tgrid > cap_ctas) tgrid = cap_ctas;
+  cdf_tile_map_kernel<<<(int)((grid + 255) / 256) < cap_ctas ? (int)((grid + 255) / 256) : cap_ctas, 256, 0, st>>>(a);
+  cdf_tile_sum_kernel<<<tgrid, 32 * kTileWarps, 0, st>>>(a);
+  cdf_classify_kernel<<<1, 1024, 0, st>>>(a);
+  cdf_tile_inc_kernel<<<tgrid, 32 * kTileWarps, 0, st>>>(a);
+  cdf_runs_kernel<<<1, 1024, 0, st>>>(a);
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e2 = cudaFuncSetAttribute(cdf_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkShared));
+      if (e2 != cudaSuccess) return (int)e2;
+      attr_set = true;
+    }
+  }
+  cdf_push_hard_kernel<<<128, 256, 0, st>>>(a);
+  cdf_walk_kernel<<<1, kWalkThreads, sizeof(WalkShared), st>>>(a);
+  if (world > 1) cdf_tile_end_kernel<<<(int)((grid + 255) / 256) < cap_ctas ? (int)((grid + 255) / 256) : cap_ctas, 256, 0, st>>>(a);
+  cdf_emit_kernel<<<tgrid, 32 * kTileWarps, 0, st>>>(a);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_stream_t stream) {
+  if (n <= 0 || !p || !cdf || !workspace) return TB_ERR_ARG;
+  // single segment [0, n): the bounds live at the end of the workspace (written on the stream)
+  const int64_t cap = tb_cdf_tile_cap(n, 1);
+  int64_t* seg = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(workspace) + local_bytes(cap) + x_layout(cap).total);
+  cdf_set_bounds_kernel<<<1, 1, 0, as_stream(stream)>>>(seg, n);
+  return tb_cdf_exact_x(p, n, seg, 1, n, cap, cdf, workspace, nullptr, stream);
+}
+
+int tb_cdf_search_x(const double* p, int64_t n_local, double* cdf, void* workspace, int64_t ntg_cap, const tb_cdf_x* x,
+                    const double* draws, int64_t m, int32_t systematic, double u0, int64_t* idx, int32_t* overflow,
+                    tb_stream_t stream) {
+  if (!workspace || m < 0 || (m > 0 && !idx) || (!systematic && m > 0 && !draws) || (systematic && !overflow)) return TB_ERR_ARG;
+  if (m == 0) return TB_OK;
+  const CdfArgs a = make_args(p, n_local, cdf, workspace, ntg_cap, x);
+  cudaStream_t st = as_stream(stream);
+  if (systematic) {
+    cudaError_t e = cudaMemsetAsync(overflow, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    cdf_search_x_kernel<1><<<stream_grid(m, kBlock, 16), kBlock, 0, st>>>(a, nullptr, m, u0, idx, overflow);
+  } else {
+    cdf_search_x_kernel<0><<<stream_grid(m, kBlock, 16), kBlock, 0, st>>>(a, draws, m, 0.0, idx, nullptr);
+  }
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+}  // extern "C"

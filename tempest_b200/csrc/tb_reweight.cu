@@ -147,39 +147,6 @@ __device__ __forceinline__ void write_probe_result(double* out, const Ess3& e, d
   out[5] = bad;
 }
 
-__global__ void __launch_bounds__(kBlock, 5)
-probe_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n, double beta,
-             ProbeWs* ws, double* __restrict__ out) {
-  __shared__ double smem[160];
-  Ess3 e; e.init();
-  double bad = 0.0;
-  probe_slice(logl, C, n, beta, e, bad);
-  block_merge_ess3(e, smem);
-  bad = block_sum(bad, smem + 100);
-  if (threadIdx.x == 0) {
-    double* p = ws->partial[blockIdx.x];
-    p[0] = e.m; p[1] = e.s1; p[2] = e.s2; p[3] = bad;
-  }
-  if (last_block_arrives(&ws->ticket)) {      // the fold of the search kernel: (m, S1, S2) identical bit for bit
-    __shared__ double s_tot[4];
-    EssFold().rows(&ws->partial[0][0], gridDim.x, 4, s_tot);
-    if (threadIdx.x == 0) { e.m = s_tot[0]; e.s1 = s_tot[1]; e.s2 = s_tot[2]; write_probe_result(out, e, s_tot[3]); }
-  }
-}
-
-__global__ void __launch_bounds__(kBlock)
-weights_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n, double beta,
-               const double* __restrict__ stats, double* __restrict__ w, int want_log) {
-  const double m = stats[0], s1 = stats[1];
-  const double lse = stats[4];
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
-    double a = __dsub_rn(__dmul_rn(__ldg(logl + s), beta), __ldg(C + s));
-    w[s] = want_log ? (a - lse) : exp(a - m) / s1;
-  }
-}
-
-// ---- device-side next-beta search ---------------------------------------------------
 // Row fold of grid_xreduce for (m, S1, S2, n_nonfinite) rows: Ess3 merges in a fixed order.
 struct EssFold {
   // all threads of the CTA; thread t merges rows t, t + B, ... in ascending order, then the fixed-order CTA merge
@@ -214,6 +181,39 @@ struct EssFold {
   }
 };
 
+__global__ void __launch_bounds__(kBlock, 5)
+probe_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n, double beta,
+             ProbeWs* ws, double* __restrict__ out) {
+  __shared__ double smem[160];
+  Ess3 e; e.init();
+  double bad = 0.0;
+  probe_slice(logl, C, n, beta, e, bad);
+  block_merge_ess3(e, smem);
+  bad = block_sum(bad, smem + 100);
+  if (threadIdx.x == 0) {
+    double* p = ws->partial[blockIdx.x];
+    p[0] = e.m; p[1] = e.s1; p[2] = e.s2; p[3] = bad;
+  }
+  if (last_block_arrives(&ws->ticket)) {      // the fold of the search kernel: (m, S1, S2) identical bit for bit
+    __shared__ double s_tot[4];
+    EssFold().rows(&ws->partial[0][0], gridDim.x, 4, s_tot);
+    if (threadIdx.x == 0) { e.m = s_tot[0]; e.s1 = s_tot[1]; e.s2 = s_tot[2]; write_probe_result(out, e, s_tot[3]); }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+weights_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n, double beta,
+               const double* __restrict__ stats, double* __restrict__ w, int want_log) {
+  const double m = stats[0], s1 = stats[1];
+  const double lse = stats[4];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride) {
+    double a = __dsub_rn(__dmul_rn(__ldg(logl + s), beta), __ldg(C + s));
+    w[s] = want_log ? (a - lse) : exp(a - m) / s1;
+  }
+}
+
+// ---- device-side next-beta search ---------------------------------------------------
 constexpr double kBetaTol = 1e-4, kBetaRtol = 1e-8, kEssTol = 0.01, kMetricAtol = 0.5;  // config.py:233-236
 constexpr int kMaxBisect = 200;                                                          // reweight.py:121
 constexpr double kTiny = 2.2250738585072014e-308;

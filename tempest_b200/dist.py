@@ -5,9 +5,9 @@ One process per GPU (torchrun).  Walker slots are block-partitioned: rank r owns
 generation, so the persistent ensemble is sharded identically; per-generation scalars and the
 mode statistics are replicated.  The data path never moves the ensemble: the collectives are
 (i) an all-gather of one (max, S1, S2) triple per ESS probe, (ii) all-reduces of histograms /
-moment sums (<= a few thousand numbers), (iii) an ownership-masked all-reduce of the N resampled
-rows (each slot's row is written by exactly one rank, every other rank contributes zeros, so the
-sum is exact and order-independent) and (iv) one (K+3)-number all-reduce per Metropolis step.
+moment sums (<= a few thousand numbers), (iii) an all-to-all of the N resampled rows (each row goes
+from the rank that stores its ancestor to the rank that owns its walker slot) and (iv) one
+(K+3)-number all-reduce per Metropolis step, fused into the step kernel over peer memory.
 Pure host logic lives here so that it can be exercised with the gloo backend on CPU.
 """
 from __future__ import annotations
@@ -85,10 +85,28 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
 
 def exchange_owned_rows(comm: Comm, rows: torch.Tensor, owned_slots: torch.Tensor, n_global: int,
                         lo: int, hi: int) -> torch.Tensor:
-    """Ownership-masked all-reduce: `rows[i]` is the payload for global slot `owned_slots[i]`
-    (each slot is owned by exactly one rank).  Returns the rows of slots [lo, hi)."""
-    full = torch.zeros((n_global, rows.shape[1]), dtype=rows.dtype, device=rows.device)
-    if owned_slots.numel():
-        full[owned_slots] = rows
-    comm.allreduce_sum_(full)
-    return full[lo:hi].contiguous()
+    """Move resampled rows to the ranks that own their walker slots: ``rows[i]`` is the payload for global slot
+    ``owned_slots[i]`` (ascending; every slot has exactly one sender).  Returns the rows of slots [lo, hi).
+
+    All-to-all of only the owned rows (each row travels once, with its slot number as an extra column):
+    N/G rows of (D+2) doubles leave every rank -- 12.6 MB at C4 on 8 GPUs -- instead of an all-reduce of the
+    zero-padded N x (D+1) table (92 MB), which made the resampling stage 7.6x slower on 8 GPUs than on one."""
+    world, per = comm.world, n_global // comm.world
+    width = int(rows.shape[1])
+    n_own = int(owned_slots.numel())
+    dest = torch.div(owned_slots, per, rounding_mode="floor")
+    send = torch.bincount(dest, minlength=world)[:world] if n_own else torch.zeros(world, dtype=torch.int64,
+                                                                                    device=rows.device)
+    counts = comm.allgather(send.to(torch.int64)).cpu()            # [src, dst]; the one host sync of the exchange
+    send_l = counts[comm.rank].tolist()
+    recv_l = counts[:, comm.rank].tolist()
+    payload = torch.empty((n_own, width + 1), dtype=rows.dtype, device=rows.device)
+    payload[:, :width] = rows
+    payload[:, width] = owned_slots.to(rows.dtype)                  # slot numbers < 2^53: exact in fp64
+    out = torch.empty((int(sum(recv_l)), width + 1), dtype=rows.dtype, device=rows.device)
+    dist.all_to_all_single(out, payload, output_split_sizes=recv_l, input_split_sizes=send_l, group=comm.group)
+    if out.shape[0] != hi - lo:
+        raise RuntimeError(f"row exchange delivered {out.shape[0]} rows for {hi - lo} slots")
+    mine = torch.empty((hi - lo, width), dtype=rows.dtype, device=rows.device)
+    mine[out[:, width].to(torch.int64) - lo] = out[:, :width]
+    return mine

@@ -239,47 +239,70 @@ class ShardedKernels(Kernels):
         raw = self.comm.allreduce_sum_(out[1:2].clone())
         return 0.5 * math.sqrt(float(raw.item()))
 
-    # -- global multinomial draws over the sharded cdf ---------------------------------------------------
-    def sharded_search(self, p: torch.Tensor, n: int, seg_begin: torch.Tensor, draws: torch.Tensor,
-                       out: torch.Tensor, name: str):
-        """Ancestor index of every (replicated) draw whose ancestor lives on this rank, -1 elsewhere.
+    # -- global exact cumulative sum + searches over the sharded weight vector (csrc/tb_cdf.cu) ------------------
+    def _cdf_tables(self, need_cap: int):
+        """Peer-mapped table memory of the sharded cdf (tile sums / classes / totals and the elements of the hard
+        tiles travel through it by NVLink stores).  One allocation sized for the ensemble's capacity."""
+        if getattr(self, "_cdf_cap", 0) >= need_cap:
+            return
+        import torch.distributed._symmetric_memory as symm
 
-        The global cdf is ordered like the single-GPU ensemble (generation-major, then slot), so the
-        same draws select the same ancestors for any number of GPUs.  ``seg_begin`` [S+1] are the local
-        start positions of this rank's per-generation segments (may be empty)."""
+        cap = int(need_cap)
+        n = int(self.lib.tb_cdf_x_table_bytes(cap)) // 8
+        buf = symm.empty(n, dtype=F64, device=self.device)
+        buf.zero_()
+        handle = symm.rendezvous(buf, torch.distributed.group.WORLD if self.comm.group is None else self.comm.group)
+        torch.cuda.synchronize()
+        self.comm.allreduce_sum_(torch.zeros(1, device=self.device))      # everyone has zeroed its tables
+        self._cdf_buf, self._cdf_handle, self._cdf_cap = buf, handle, cap
+        self._cdf_seq = 0
+
+    def cdf_x(self, p: torch.Tensor, n: int, seg_begin: torch.Tensor, n_global: int, name: str):
+        """numpy's sequential cumsum of the GLOBAL weight vector (generation-major, rank-minor: the order of the
+        single-GPU ensemble), this rank's part in ``cdf``.  ``seg_begin`` [S+1]: local start positions of this rank's
+        per-generation segments; ``n_global``: global element count (the same on every rank)."""
         S = int(seg_begin.numel()) - 1
-        if n > 0 and p.numel() > 0:
-            cdf = self.cdf(p, n, name)
-            csum = torch.cat([torch.zeros(1, dtype=F64, device=self.device), cdf])   # csum[j] = sum of p[:j]
-            before = csum[seg_begin[:-1]]                                           # local sum before each segment
-            seg_tot = csum[seg_begin[1:]] - before
-        else:
-            n, cdf = 0, None
-            before = torch.zeros(S, dtype=F64, device=self.device)
-            seg_tot = torch.zeros(S, dtype=F64, device=self.device)
-        tot = self.comm.allgather(seg_tot).cpu().numpy()          # [G, S]
-        # running sum in global order: generation-major, rank-minor (identical on every rank)
-        flat = tot.T.reshape(-1)
-        goff = np.concatenate([[0.0], np.cumsum(flat)])
-        total = float(goff[-1])
-        start = goff[:-1].reshape(S, self.comm.world)[:, self.comm.rank].copy()      # global value before my segment
-        if n == 0:
-            out.fill_(-1)
-            return out, total
-        seg_start = torch.as_tensor(start, dtype=F64).to(self.device)
-        seg_shift = seg_start - before
-        m = int(draws.numel())
-        if m >= 1 << 16 and n >= 1 << 12:
-            bits = max(10, min(20, (m // 8).bit_length() - 1))
-            guide = self.ws.bytes("search_guide", self.lib.tb_search_guide_bytes(bits))
-            _lib.check(self.lib.tb_search_right_sharded_guided(ptr(cdf), n, ptr(seg_begin), ptr(seg_shift),
-                                                               ptr(seg_start), S, total, ptr(draws), m, ptr(guide), bits,
-                                                               ptr(out), stream_ptr()), "tb_search_right_sharded_guided")
-            return out, total
-        _lib.check(self.lib.tb_search_right_sharded(ptr(cdf), n, ptr(seg_begin), ptr(seg_shift), ptr(seg_start), S,
-                                                    total, ptr(draws), m, ptr(out), stream_ptr()),
-                   "tb_search_right_sharded")
-        return out, total
+        hint = max(self.ws.hint * self.comm.world, int(n_global), 1)
+        self._cdf_tables(int(self.lib.tb_cdf_tile_cap(hint, 64 * self.comm.world)))
+        cap = self._cdf_cap
+        if int(self.lib.tb_cdf_tile_cap(int(n_global), S * self.comm.world)) > cap:
+            raise RuntimeError("sharded cdf: tile table capacity exceeded")
+        ws = self.ws.bytes("cdfx_" + name, self.lib.tb_cdf_x_workspace_bytes(cap))
+        cdf = self.ws.f64(name, max(n, 1))
+        self._cdf_seq += 1
+        x = _lib.TbCdfX()
+        x.rank, x.world, x.seq = self.comm.rank, self.comm.world, self._cdf_seq
+        for r in range(self.comm.world):
+            x.peer[r] = int(self._cdf_handle.buffer_ptrs[r])
+        _lib.check(self.lib.tb_cdf_exact_x(ptr(p) if n else None, n, ptr(seg_begin), S, int(n_global), cap, ptr(cdf),
+                                           ptr(ws), C.byref(x), stream_ptr()), "tb_cdf_exact_x")
+        return dict(p=p, n=n, cdf=cdf, ws=ws, cap=cap, x=x)
+
+    def search_x(self, h: dict, draws: Optional[torch.Tensor], m: int, out: torch.Tensor, systematic: bool = False,
+                 u0: float = 0.0) -> torch.Tensor:
+        """Local ancestor index of every (replicated) draw whose ancestor lives on this rank, -1 elsewhere."""
+        ovf = self.ws.i32("cdfx_ovf", 1)
+        _lib.check(self.lib.tb_cdf_search_x(ptr(h["p"]) if h["n"] else None, h["n"], ptr(h["cdf"]), ptr(h["ws"]),
+                                            h["cap"], C.byref(h["x"]), ptr(draws), int(m), int(systematic), float(u0),
+                                            ptr(out), ptr(ovf), stream_ptr()), "tb_cdf_search_x")
+        st = h["ws"][:64].view(torch.int32).cpu().numpy()          # {tiles, segments, runs, hard tiles, error}
+        if st[4] != 0:
+            raise RuntimeError(f"sharded exact cdf failed with code {int(st[4])} (3: a peer GPU did not answer, "
+                               f"4/5: table capacity, 6: refuted binade hypothesis); tiles={int(st[0])}, hard={int(st[3])}")
+        if systematic and int(ovf.item()):
+            raise IndexError("systematic resampling walked past the last weight (tools.py:223-225)")
+        self.last_cdf_status = st
+        return out
+
+    def sharded_search(self, p: torch.Tensor, n: int, seg_begin: torch.Tensor, draws: torch.Tensor,
+                       out: torch.Tensor, name: str, n_global: Optional[int] = None):
+        """Ancestor index of every (replicated) multinomial draw whose ancestor lives on this rank, -1 elsewhere;
+        identical to numpy's ``choice`` on the global weight vector for any number of GPUs."""
+        if n_global is None:
+            n_global = self.g_int(n)
+        h = self.cdf_x(p, n, seg_begin, n_global, name)
+        self.search_x(h, draws, int(draws.numel()), out)
+        return out, None
 
 
 def sharded_mode_moments(core, idx, counts, n_trim_local: int, m_total: int, cmean, scatter):
@@ -301,13 +324,17 @@ def sharded_mode_moments(core, idx, counts, n_trim_local: int, m_total: int, cme
     k.comm.allreduce_sum_(scatter)
 
 
-def sharded_resample(core, weights: torch.Tensor, draws: torch.Tensor):
-    """N global multinomial draws; returns this rank's block of resampled (u, logl) rows."""
+def sharded_resample(core, weights: torch.Tensor, draws: Optional[torch.Tensor], systematic: bool = False,
+                     u0: float = 0.0):
+    """N global draws (multinomial: replicated uniforms; systematic: one uniform); returns this rank's block of
+    resampled (u, logl) rows.  Every rank searches all N draws in the global exact cdf, gathers the rows whose
+    ancestors it stores and sends each to the rank that owns the walker slot."""
     k, ens, comm = core.k, core.ensemble, core.comm
     n_glob = core.n_global
     d = ens.n_dim
     idx = k.ws.i64("res_idx", n_glob)
-    k.sharded_search(weights, ens.n_total, core.generation_bounds(), draws, idx, "cdf")
+    h = k.cdf_x(weights, ens.n_total, core.generation_bounds(), ens.n_total_global, "cdf")
+    k.search_x(h, draws, n_glob, idx, systematic=systematic, u0=u0)
     own = torch.nonzero(idx >= 0).flatten()
     rows = torch.empty((own.numel(), d + 1), dtype=F64, device=core.device)
     if own.numel():

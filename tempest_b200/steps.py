@@ -742,7 +742,7 @@ class Trainer:
         if k.sharded:
             # segments of the trimmed set per generation (trim indices are ascending = generation-major)
             seg_begin = torch.searchsorted(idx, core.generation_bounds())
-            k.sharded_search(wt, n_trim, seg_begin, draws, didx, "train_cdf")
+            k.sharded_search(wt, n_trim, seg_begin, draws, didx, "train_cdf", n_global=n_trim_glob)
         else:
             cdf = k.cdf(wt, n_trim, "train_cdf")
             k.search_right(cdf, n_trim, draws, didx)
@@ -840,11 +840,12 @@ class Resampler:
             st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
             return
         if k.sharded:
-            if core.config.resample != "mult":
-                raise NotImplementedError("systematic resampling is not sharded yet; use resample='mult' on >1 GPU")
             from .sharded import sharded_resample
 
-            u, logl = sharded_resample(core, weights, core.rng.resample_u(core.n_global))
+            if core.config.resample == "mult":
+                u, logl = sharded_resample(core, weights, core.rng.resample_u(core.n_global))
+            else:
+                u, logl = sharded_resample(core, weights, None, systematic=True, u0=core.rng.resample_u0())
             st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
             return
         cdf = k.cdf(weights, ens.n_total)
@@ -935,7 +936,22 @@ class Mutator:
             if k.sharded:
                 any_bad = bool(k.g_int(int(any_bad)))
                 if any_bad:
-                    raise NotImplementedError("infinite log-likelihoods at warm-up are not handled on >1 GPU yet")
+                    # rare: replicate the generation (rank-major = slot order), apply mutate.py:122-148 to the
+                    # replicated table with the replicated picks, keep this rank's block of slots
+                    U = k.comm.allgather(u).reshape(core.n_global, d)
+                    L = k.comm.allgather(logl).reshape(core.n_global)
+                    badg = torch.isinf(L)
+                    every = torch.arange(core.n_global, device=core.device)
+                    inf_idx, fin_idx = every[badg], every[~badg]
+                    if fin_idx.numel() > 0:
+                        pick = core.rng.inf_pick(fin_idx, int(inf_idx.numel()))
+                        U[inf_idx] = U[pick]
+                        L[inf_idx] = L[pick]
+                    lo = core.slot_offset
+                    u.copy_(U[lo:lo + n])
+                    logl.copy_(L[lo:lo + n])
+                    st.set_current("logz", st.raw("logz") + math.log(fin_idx.numel() / core.n_global))
+                    return
             if any_bad:                                 # mutate.py:122-148 (rare; bookkeeping on device tensors)
                 every = torch.arange(n, device=core.device)
                 inf_idx, fin_idx = every[bad], every[~bad]

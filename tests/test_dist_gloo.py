@@ -1,6 +1,6 @@
 """Host-side logic of the sharded (multi-GPU) path, exercised with world_size = 2 on the gloo
-backend (CPU): shard bounds, rank-order merge of ESS triples, the ownership-masked all-reduce
-that moves resampled rows to their slot owners, and the padded variable-length all-gather."""
+backend (CPU): shard bounds, rank-order merge of ESS triples, the all-to-all that moves resampled
+rows to their slot owners, and the padded variable-length all-gather."""
 import math
 import os
 import socket
@@ -36,7 +36,12 @@ def _worker(rank, world, port, ret):
         table = torch.as_tensor(rng.random((n, d + 1)))
         owned = torch.arange(rank, n, world)
         mine = exchange_owned_rows(comm, table[owned].clone(), owned, n, lo, hi)
-        assert torch.equal(mine, table[lo:hi])                      # exact: x + 0 = x
+        assert torch.equal(mine, table[lo:hi])
+        # uneven ownership (rank 0 holds the ancestors of 3/4 of the slots), incl. a rank that sends nothing to a peer
+        cut = (3 * n) // 4
+        owned = torch.arange(0, cut) if rank == 0 else torch.arange(cut, n)
+        mine = exchange_owned_rows(comm, table[owned].clone(), owned, n, lo, hi)
+        assert torch.equal(mine, table[lo:hi])
         # padded all-gather of variable-length shards, rank-major
         part = torch.arange(rank * 10, rank * 10 + 3 + rank, dtype=torch.float64).reshape(-1, 1)
         allp = comm.allgather_rows(part)

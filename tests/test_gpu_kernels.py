@@ -381,7 +381,8 @@ def test_production_variates_match_numpy_restatement(env, shape):
     g, z, a = _variates(env, n, d, shape, 0, step, attempt, seed, it, off)
     slots = off + np.arange(n, dtype=np.uint64)
     zr = ph.step_normals(seed, it, slots, step, attempt, d)
-    np.testing.assert_allclose(z.cpu().numpy(), zr, rtol=0, atol=2e-5)
+    dz = np.abs(z.cpu().numpy() - zr)
+    assert dz.max() < 2e-4 and np.quantile(dz, 0.9999) < 1e-5
     gr, ar, margin = ph.step_gamma(seed, it, slots, step, shape)
     gd, ad = g.cpu().numpy(), a.cpu().numpy()
     # a Marsaglia-Tsang comparison within 1e-5 of its threshold may resolve differently (fp32 normal inside it)
