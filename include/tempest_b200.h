@@ -443,6 +443,42 @@ int tb_debug_variates(uint64_t seed, uint64_t iteration, int64_t slot_offset, in
 int tb_philox_uniform(uint64_t seed, uint64_t iteration, uint32_t purpose, int64_t offset,
                       int64_t n, double* out, tb_stream_t stream);
 
+/* volume_variation's rank test / regularisation / final value on the device (tools.py:101-115), so that the cv
+ * diagnostic needs no host round trip: after tb_chol_inv of a copy of cov, tb_vv_regularise sets flags[0] =
+ * rank-deficient and then adds 1e-6 trace(cov) I to cov, and copies cov to work for the second tb_chol_inv;
+ * tb_vv_finish writes result[0] = 0.5 sqrt(raw[0]) or 1e10 when that inverse failed as well. */
+int tb_vv_regularise(double* cov, double* work, int32_t d, const int32_t* info, const double* norms, int32_t* flags,
+                     tb_stream_t stream);
+int tb_vv_finish(const double* raw, const int32_t* info2, const double* norms2, const int32_t* flags, double* result,
+                 tb_stream_t stream);
+
+/* Small-message collectives over peer memory for sharded runs (csrc/tb_xcoll.cu): two kernels on the caller's
+ * stream, no host synchronisation.  peer[r] = rank r's staging buffer (tb_xcoll_buffer_bytes(cap_bytes) bytes of
+ * zero-initialised symmetric memory, cap_bytes a multiple of 16) as addressed from this device; seq = call number
+ * (>= 1, +1 per call on every rank); ticket = a zeroed device uint32 private to this rank.  dtype 0 f64, 1 i64,
+ * 2 i32.  All-reduce folds the ranks' payloads in rank order: bitwise identical results on every rank.
+ * *err (device int32, nullable) receives 3 if a peer did not answer within the spin budget. */
+typedef struct tb_xcoll {
+  int32_t rank, world;
+  uint64_t seq;
+  uint64_t cap_bytes;
+  void* ticket;
+  void* peer[8];
+} tb_xcoll;
+size_t tb_xcoll_buffer_bytes(size_t cap_bytes);
+int tb_xcoll_allreduce_sum(void* data, int64_t n, int32_t dtype, const tb_xcoll* x, int32_t* err, tb_stream_t stream);
+int tb_xcoll_allgather(const void* src, int64_t nbytes, void* out, const tb_xcoll* x, int32_t* err, tb_stream_t stream);
+/* Resampled rows of a sharded run (resample.py:86-96): idx[n_glob] holds, for every global draw k, the LOCAL index
+ * of its ancestor or -1 (tb_cdf_search_x).  Row k = (u[idx k], logl[idx k]) is stored over NVLink straight into the
+ * active-set buffer of the rank that owns walker slot k (k / per), then the stream is held until every rank's rows
+ * have arrived.  x->peer[r]: rank r's row buffer (tb_xrows_buffer_bytes(per, d) bytes of zeroed symmetric memory);
+ * the rows of call number seq land at double offset tb_xrows_offset(per, d, seq & 1): u[per][d] then logl[per].
+ * (x->cap_bytes is ignored.) */
+size_t tb_xrows_buffer_bytes(int64_t per, int32_t d);
+int64_t tb_xrows_offset(int64_t per, int32_t d, int32_t parity);
+int tb_xrows_scatter(const double* hu, const double* hl, int32_t d, const int64_t* idx, int64_t n_glob, int64_t per,
+                     const tb_xcoll* x, int32_t* err, tb_stream_t stream);
+
 /* measurement aid (bench.py): one launch of 8 * n_SM CTAs x 256 threads, each running eight independent
  * register-resident fp64 FMA chains for `iters` iterations = tb_fp64_peak_flops(iters) flop; timed by the
  * caller with CUDA events it gives the fp64 FMA peak the mutation kernel's roofline is quoted against */

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build" + os.environ.get("TB_OBJ_SUFFIX", ""))
 LIB = os.path.join(LIBDIR, os.environ.get("TB_LIB_NAME", "libtempest_b200.so"))   # TB_LIB_NAME / TB_NVCC_EXTRA: A/B builds
-SOURCES = ["tb_reweight.cu", "tb_resample.cu", "tb_cdf.cu", "tb_moments.cu", "tb_linalg.cu", "tb_mcmc.cu", "tb_cluster.cu",
+SOURCES = ["tb_reweight.cu", "tb_resample.cu", "tb_cdf.cu", "tb_xcoll.cu", "tb_moments.cu", "tb_linalg.cu", "tb_mcmc.cu", "tb_cluster.cu",
            "tb_mcmc_fast_a.cu", "tb_mcmc_fast_b.cu", "tb_mcmc_fast_c.cu", "tb_mcmc_fast_d.cu", "tb_mcmc_fast_e.cu",
            "tb_mcmc_fast_f.cu", "tb_mcmc_wide.cu"]
 NVCC_FLAGS = [

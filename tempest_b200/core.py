@@ -41,6 +41,7 @@ class SamplerCore:
             lo, hi = shard_bounds(self.n_global, self.comm.world, self.comm.rank)
             self.slot_offset, self.n_local = lo, hi - lo
             self.k = ShardedKernels(self.device, self.comm)
+            self.k.defer_checks = True
         else:
             self.slot_offset, self.n_local = 0, self.n_global
             self.k = Kernels(self.device)
@@ -177,6 +178,9 @@ class SamplerCore:
                 self.k_side.volume_variation_mid(self.ensemble.u, w_cv, n, self.ensemble.n_dim)
 
     def end_cv(self) -> None:
+        if getattr(self, "_cv_sharded", False):
+            self._cv_sharded = False
+            self.state.set_current("cv", self.k.volume_variation_result())
         if self._cv_pending is not None:
             self._cv_pending = None
             with torch.cuda.stream(self.side):
@@ -275,6 +279,8 @@ class SamplerCore:
         self._stage("mutate")
         self.mutator.run(mode_stats)
         self.end_cv()
+        if self.comm.on:
+            self.k.check_pending()          # status words of this iteration's sharded cdf calls / peer collectives
         self._stage("commit")
         # commit (state_manager.py:356-416): particles to the device ensemble, scalars to host lists
         st = self.state
@@ -446,7 +452,7 @@ class SamplerCore:
         u, logl = ens.u[:n], ens.logl[:n]
         idx = None
         if trim_importance_weights:                        # core.py:210-220
-            idx, w = k.trim(w, n, ess=ess_trim, bins=bins_trim)
+            idx, w = k.trim(w, n, ess=ess_trim, bins=bins_trim, n_global=ens.n_total_global)
             u, logl = u[idx], logl[idx]
         if resample and self.comm.on:                      # core.py:222-231 over the global (trimmed) weight vector
             m_loc = int(w.numel())
@@ -463,6 +469,7 @@ class SamplerCore:
             order = torch.argsort(allp)                    # every rank returns the sample in position order
             x, logl = allx[order], alll[order]
             w = torch.full((m,), 1.0 / m, dtype=F64, device=self.device)
+            k.check_pending()
             out = tuple(self._to_host(t) for t in (x, w, logl))
             if logw is not None:
                 logw = self.comm.allgather_rows(torch.as_tensor(logw).to(self.device)).cpu().numpy()

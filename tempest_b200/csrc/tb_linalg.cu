@@ -87,6 +87,37 @@ __global__ void add_trace_reg_kernel(double* __restrict__ cov, int d, double fac
   for (int i = threadIdx.x; i < d; i += blockDim.x) cov[i * d + i] += factor * tr;
 }
 
+// volume_variation's rank test and regularisation without a host round trip (tools.py:101-110).  After a first
+// chol_inv of a copy of cov (info / norms): flags[0] = "matrix_rank(cov) < d" (Cholesky failure, or
+// |A|_F |A^-1|_F >= 1 / (d eps), an upper bound of cond_2); if set, cov += 1e-6 trace(cov) I.  work = cov.
+__global__ void __launch_bounds__(128)
+vv_regularise_kernel(double* __restrict__ cov, double* __restrict__ work, int d, const int* __restrict__ info,
+                     const double* __restrict__ norms, int* __restrict__ flags) {
+  __shared__ double tr;
+  __shared__ int singular;
+  if (threadIdx.x == 0) {
+    const double n0 = norms[0], n1 = norms[1];
+    singular = (info[0] != 0 || !isfinite(n0) || !isfinite(n1) || n0 * n1 >= 1.0 / ((double)d * 2.220446049250313e-16)) ? 1 : 0;
+    flags[0] = singular;
+    double t = 0.0;
+    for (int i = 0; i < d; ++i) t += cov[i * d + i];
+    tr = t;
+  }
+  __syncthreads();
+  if (singular) for (int i = threadIdx.x; i < d; i += blockDim.x) cov[i * d + i] += 1e-6 * tr;
+  __syncthreads();
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) work[e] = cov[e];
+}
+
+// cv = 0.5 sqrt(raw), or 1e10 when the regularised matrix could not be inverted either (tools.py:108-110)
+__global__ void vv_finish_kernel(const double* __restrict__ raw, const int* __restrict__ info2, const double* __restrict__ norms2,
+                                 const int* __restrict__ flags, double* __restrict__ result) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const bool failed = flags[0] && (info2[0] == 2 || !isfinite(norms2[0]) || !isfinite(norms2[1]));
+    result[0] = (failed || info2[0] == 2) ? 1e10 : 0.5 * sqrt(raw[0]);
+  }
+}
+
 // fp64 FMA peak probe for the roofline of the mutation kernel: eight independent register-resident DFMA chains
 // per thread, nothing else in the loop (the denominator MEASURED_PEAKS.json does not carry)
 __global__ void __launch_bounds__(256)
@@ -105,6 +136,22 @@ fp64_peak_kernel(int iters, double seed, double* __restrict__ out) {
 }  // namespace
 
 extern "C" {
+
+int tb_vv_regularise(double* cov, double* work, int32_t d, const int32_t* info, const double* norms, int32_t* flags,
+                     tb_stream_t stream) {
+  if (!cov || !work || d <= 0 || d > 128 || !info || !norms || !flags) return TB_ERR_ARG;
+  vv_regularise_kernel<<<1, 128, 0, as_stream(stream)>>>(cov, work, d, info, norms, flags);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_vv_finish(const double* raw, const int32_t* info2, const double* norms2, const int32_t* flags, double* result,
+                 tb_stream_t stream) {
+  if (!raw || !info2 || !norms2 || !flags || !result) return TB_ERR_ARG;
+  vv_finish_kernel<<<1, 32, 0, as_stream(stream)>>>(raw, info2, norms2, flags, result);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
 
 int64_t tb_fp64_peak_flops(int32_t iters) {
   return (int64_t)2 * 8 * (int64_t)iters * 256 * (int64_t)tb::sm_count() * 8;

@@ -28,8 +28,14 @@ class Comm:
         self.world = dist.get_world_size(group) if self.on else 1
         self.rank = dist.get_rank(group) if self.on else 0
 
+    # `fast`: small-message collectives over NVLink peer memory (sharded.PeerCollectives), attached by the device
+    # layer when symmetric memory is available: stream-ordered kernels instead of NCCL calls (30-50 us each).
+    fast = None
+
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
         if self.on:
+            if self.fast is not None and self.fast.takes(t):
+                return self.fast.allreduce_sum_(t)
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
@@ -38,6 +44,8 @@ class Comm:
         if not self.on:
             return t.unsqueeze(0)
         flat = t.contiguous().reshape(-1)
+        if self.fast is not None and self.fast.takes(flat):
+            return self.fast.allgather(flat).reshape((self.world,) + tuple(t.shape))
         out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, flat, group=self.group)
         return out.reshape((self.world,) + tuple(t.shape))

@@ -20,12 +20,69 @@ from .ensemble import PersistentEnsemble, ptr, stream_ptr
 from .steps import _EPS, F64, Kernels
 
 
+class PeerCollectives:
+    """All-reduce (sum) / all-gather of small tensors through peer-mapped staging buffers (csrc/tb_xcoll.cu): two
+    kernels on the current stream per call, no host synchronisation, bitwise identical results on every rank
+    (payloads are folded in rank order).  Every rank must issue the same sequence of calls."""
+
+    CAP_BYTES = 4 << 20
+    DTYPES = {torch.float64: 0, torch.int64: 1, torch.int32: 2}
+
+    def __init__(self, lib, device: torch.device, comm: Comm):
+        import torch.distributed._symmetric_memory as symm
+
+        self.lib, self.device, self.comm = lib, device, comm
+        n = int(lib.tb_xcoll_buffer_bytes(self.CAP_BYTES)) // 8
+        self.buf = symm.empty(n, dtype=F64, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, torch.distributed.group.WORLD if comm.group is None else comm.group)
+        torch.cuda.synchronize()
+        torch.distributed.all_reduce(torch.zeros(1, device=device))          # everyone has zeroed its staging buffer
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.x = _lib.TbXcoll()
+        self.x.rank, self.x.world, self.x.seq, self.x.cap_bytes = comm.rank, comm.world, 0, self.CAP_BYTES
+        self.x.ticket = self.ticket.data_ptr()
+        for r in range(comm.world):
+            self.x.peer[r] = int(self.handle.buffer_ptrs[r])
+
+    def takes(self, t: torch.Tensor) -> bool:
+        return (t.is_cuda and t.is_contiguous() and t.numel() > 0 and t.element_size() >= 4
+                and t.numel() * t.element_size() <= self.CAP_BYTES)
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        code = self.DTYPES.get(t.dtype)
+        if code is None:
+            torch.distributed.all_reduce(t, group=self.comm.group)
+            return t
+        self.x.seq += 1
+        _lib.check(self.lib.tb_xcoll_allreduce_sum(ptr(t), t.numel(), code, C.byref(self.x), ptr(self.err), stream_ptr()),
+                   "tb_xcoll_allreduce_sum")
+        return t
+
+    def allgather(self, flat: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.comm.world * flat.numel(), dtype=flat.dtype, device=flat.device)
+        self.x.seq += 1
+        _lib.check(self.lib.tb_xcoll_allgather(ptr(flat), flat.numel() * flat.element_size(), ptr(out), C.byref(self.x),
+                                               ptr(self.err), stream_ptr()), "tb_xcoll_allgather")
+        return out
+
+    def check(self) -> None:
+        if int(self.err.item()):
+            raise RuntimeError("peer-memory collective timed out: a peer GPU did not answer")
+
+
 class ShardedKernels(Kernels):
     def __init__(self, device: torch.device, comm: Comm):
         super().__init__(device)
         self.comm = comm
         self.sharded = True
         self.xgpu = self._setup_xgpu()
+        if self.xgpu is not None and comm.fast is None:
+            import os
+
+            if os.environ.get("TEMPEST_B200_PEER_COLLECTIVES", "1") != "0":
+                comm.fast = PeerCollectives(self.lib, device, comm)
 
     # -- peer-mapped exchange buffers for the in-kernel collectives (tb_xgpu.cuh) --------------------
     def _setup_xgpu(self):
@@ -99,27 +156,25 @@ class ShardedKernels(Kernels):
         return s1, s2 / (s1 * s1)
 
     def g_hist(self, w, n: int):
-        cnt = self.ws.i64("trim_cnt", 2048)
-        s1 = self.ws.f64("trim_s1", 2048)
-        s2 = self.ws.f64("trim_s2", 2048)
-        _lib.check(self.lib.tb_binade_hist(ptr(w), n, ptr(cnt), ptr(s1), ptr(s2), stream_ptr()), "tb_binade_hist")
-        for t in (cnt, s1, s2):
-            self.comm.allreduce_sum_(t)
-        return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
+        buf, cnt, s1, s2 = self._hist_buffers("trim_hist")
+        if n > 0:
+            _lib.check(self.lib.tb_binade_hist(ptr(w), n, ptr(cnt), ptr(s1), ptr(s2), stream_ptr()), "tb_binade_hist")
+        else:
+            buf.zero_()
+        self.comm.allreduce_sum_(cnt)            # counts (int64) and the two sum columns (fp64, contiguous): two
+        self.comm.allreduce_sum_(buf[2048:])     # collectives, one read-back
+        return self._hist_to_host(buf)
 
     def g_subhist(self, w, n: int, binade: int):
-        cnt = self.ws.i64("trim_cnt2", 2048)
-        s1 = self.ws.f64("trim_s1b", 2048)
-        s2 = self.ws.f64("trim_s2b", 2048)
+        buf, cnt, s1, s2 = self._hist_buffers("trim_hist2")
         if n > 0:
             _lib.check(self.lib.tb_subbin_hist(ptr(w), n, int(binade), ptr(cnt), ptr(s1), ptr(s2), stream_ptr()),
                        "tb_subbin_hist")
         else:
-            for t in (cnt, s1, s2):
-                t.zero_()
-        for t in (cnt, s1, s2):
-            self.comm.allreduce_sum_(t)
-        return cnt.cpu().numpy().astype(np.int64), s1.cpu().numpy(), s2.cpu().numpy()
+            buf.zero_()
+        self.comm.allreduce_sum_(cnt)
+        self.comm.allreduce_sum_(buf[2048:])
+        return self._hist_to_host(buf)
 
     def bucket_pair_sharded(self, base, rows, mult, n: int, d: int, rank_lo: int, same: bool, lo_value: float,
                             hi_value: float, unit_map: bool, build: bool, out: torch.Tensor) -> bool:
@@ -153,7 +208,8 @@ class ShardedKernels(Kernels):
         stage(1)
         stage(2)
         sel = bws[o1: o1 + 24 * d].view(torch.int32).reshape(d, 6)
-        allc = self.comm.allgather(sel[:, 4:6].contiguous()).cpu().numpy()        # [G, d, (count, overflow)]
+        allc_dev = self.comm.allgather(sel[:, 4:6].contiguous())                  # [G, d, (count, overflow)]
+        allc = allc_dev.cpu().numpy()
         counts = allc[:, :, 0].astype(np.int64)
         totals = counts.sum(axis=0)
         if allc[:, :, 1].any() or (totals > cap).any():
@@ -162,21 +218,16 @@ class ShardedKernels(Kernels):
         if maxc > 0:
             cval = bws[o2: o2 + 8 * d * cap].view(F64).reshape(d, cap)
             cmul = bws[o3: o3 + 4 * d * cap].view(torch.int32).reshape(d, cap)
-            gv = self.comm.allgather(cval[:, :maxc].contiguous()).reshape(-1)        # [G, d, maxc]
-            gm = self.comm.allgather(cmul[:, :maxc].contiguous()).reshape(-1)
-            src, dst = [], []
-            for c in range(d):
-                pos = 0
-                for r in range(G):
-                    k_ = int(counts[r, c])
-                    if k_:
-                        src.append((r * d + c) * maxc + np.arange(k_))
-                        dst.append(c * cap + pos + np.arange(k_))
-                        pos += k_
-            src_t = torch.as_tensor(np.concatenate(src)).to(self.device)
-            dst_t = torch.as_tensor(np.concatenate(dst)).to(self.device)
-            cval.reshape(-1)[dst_t] = gv[src_t]
-            cmul.reshape(-1)[dst_t] = gm[src_t]
+            gv = self.comm.allgather(cval[:, :maxc].contiguous())                 # [G, d, maxc]
+            gm = self.comm.allgather(cmul[:, :maxc].contiguous())
+            # merge on the device: column c receives the ranks' candidates in rank order
+            cnt_dev = allc_dev[:, :, 0].to(torch.int64)                            # [G, d]
+            mask = (torch.arange(maxc, device=self.device)[None, None, :] < cnt_dev[:, :, None]).permute(1, 0, 2)
+            mask = mask.reshape(d, G * maxc)
+            pos = torch.cumsum(mask, dim=1) - 1
+            dst = (torch.arange(d, device=self.device)[:, None] * cap + pos)[mask]
+            cval.reshape(-1)[dst] = gv.permute(1, 0, 2).reshape(d, G * maxc)[mask]
+            cmul.reshape(-1)[dst] = gm.permute(1, 0, 2).reshape(d, G * maxc)[mask]
         sel[:, 4] = torch.as_tensor(totals.astype(np.int32)).to(self.device)
         stage(3, out, ovf)
         return int(ovf.item()) == 0
@@ -239,6 +290,43 @@ class ShardedKernels(Kernels):
         raw = self.comm.allreduce_sum_(out[1:2].clone())
         return 0.5 * math.sqrt(float(raw.item()))
 
+    def volume_variation_async(self, u, w, n: int, d: int) -> None:
+        """tools.py:58-117 enqueued without a host round trip (ESS mode: cv is a diagnostic, read after the mutation):
+        partial moments + all-reduces, Cholesky / rank decision / regularisation / second inverse on the device."""
+        lib, st = self.lib, stream_ptr()
+        if n * self.comm.world < d + 1:
+            self._vv_async = "small"
+            return
+        ws = self.ws.bytes("mom", lib.tb_moments_workspace_bytes(d))
+        mean, cov = self.ws.f64("vv_mean", d), self.ws.f64("vv_cov", d * d)
+        work, inv = self.ws.f64("vv_work", d * d), self.ws.f64("vv_inv", d * d)
+        info, info2, flags = self.ws.i32("vv_info", 1), self.ws.i32("vv_info2", 1), self.ws.i32("vv_flags", 4)
+        norms, norms2 = self.ws.f64("vv_norms", 3), self.ws.f64("vv_norms2", 3)
+        _lib.check(lib.tb_moments_partial(ptr(u), None, ptr(w), None, n, d, 1.0, 1, 0, ptr(ws), ptr(mean), None, st),
+                   "tb_moments_partial")
+        self.comm.allreduce_sum_(mean)
+        _lib.check(lib.tb_moments_partial(ptr(u), None, ptr(w), None, n, d, 1.0, 0, 1, ptr(ws), ptr(mean), ptr(cov), st),
+                   "tb_moments_partial")
+        self.comm.allreduce_sum_(cov)
+        work.copy_(cov)
+        _lib.check(lib.tb_chol_inv(ptr(work), d, 1, None, ptr(inv), ptr(info), ptr(norms), st), "tb_chol_inv")
+        _lib.check(lib.tb_vv_regularise(ptr(cov), ptr(work), d, ptr(info), ptr(norms), ptr(flags), st), "tb_vv_regularise")
+        _lib.check(lib.tb_chol_inv(ptr(work), d, 1, None, ptr(inv), ptr(info2), ptr(norms2), st), "tb_chol_inv")
+        out = self.ws.f64("vv_out", 2)
+        _lib.check(lib.tb_mahalanobis_cv(ptr(u), ptr(w), n, d, ptr(mean), ptr(inv), ptr(self._reduce_ws), ptr(out), st),
+                   "tb_mahalanobis_cv")
+        raw = self.ws.f64("vv_raw", 2)
+        raw[:1].copy_(out[1:2])
+        self.comm.allreduce_sum_(raw[:1])
+        res = self.ws.f64("vv_res", 2)
+        _lib.check(lib.tb_vv_finish(ptr(raw), ptr(info2), ptr(norms2), ptr(flags), ptr(res), st), "tb_vv_finish")
+        self._vv_async = "enqueued"
+
+    def volume_variation_result(self) -> float:
+        if self._vv_async == "small":
+            return 1e10
+        return float(self.ws.f64("vv_res", 2)[0].item())
+
     # -- global exact cumulative sum + searches over the sharded weight vector (csrc/tb_cdf.cu) ------------------
     def _cdf_tables(self, need_cap: int):
         """Peer-mapped table memory of the sharded cdf (tile sums / classes / totals and the elements of the hard
@@ -285,14 +373,28 @@ class ShardedKernels(Kernels):
         _lib.check(self.lib.tb_cdf_search_x(ptr(h["p"]) if h["n"] else None, h["n"], ptr(h["cdf"]), ptr(h["ws"]),
                                             h["cap"], C.byref(h["x"]), ptr(draws), int(m), int(systematic), float(u0),
                                             ptr(out), ptr(ovf), stream_ptr()), "tb_cdf_search_x")
-        st = h["ws"][:64].view(torch.int32).cpu().numpy()          # {tiles, segments, runs, hard tiles, error}
-        if st[4] != 0:
-            raise RuntimeError(f"sharded exact cdf failed with code {int(st[4])} (3: a peer GPU did not answer, "
-                               f"4/5: table capacity, 6: refuted binade hypothesis); tiles={int(st[0])}, hard={int(st[3])}")
-        if systematic and int(ovf.item()):
-            raise IndexError("systematic resampling walked past the last weight (tools.py:223-225)")
-        self.last_cdf_status = st
+        self._pending_status = getattr(self, "_pending_status", [])
+        self._pending_status.append((h["ws"][:64].view(torch.int32), ovf if systematic else None))
+        if not self.defer_checks:
+            self.check_pending()
         return out
+
+    defer_checks = False      # the sampler sets it: status words are then read once per iteration (check_pending)
+
+    def check_pending(self) -> None:
+        """Read the status words of the sharded cdf calls since the last check (one host round trip for all)."""
+        pend, self._pending_status = getattr(self, "_pending_status", []), []
+        for status, ovf in pend:
+            st = status.cpu().numpy()                                 # {tiles, segments, runs, hard tiles, error}
+            self.last_cdf_status = st
+            if st[4] != 0:
+                raise RuntimeError(f"sharded exact cdf failed with code {int(st[4])} (3: a peer GPU did not answer, "
+                                   f"4/5: table capacity, 6: refuted binade hypothesis); tiles={int(st[0])}, "
+                                   f"hard={int(st[3])}")
+            if ovf is not None and int(ovf.item()):
+                raise IndexError("systematic resampling walked past the last weight (tools.py:223-225)")
+        if self.comm.fast is not None:
+            self.comm.fast.check()
 
     def sharded_search(self, p: torch.Tensor, n: int, seg_begin: torch.Tensor, draws: torch.Tensor,
                        out: torch.Tensor, name: str, n_global: Optional[int] = None):
@@ -324,17 +426,51 @@ def sharded_mode_moments(core, idx, counts, n_trim_local: int, m_total: int, cme
     k.comm.allreduce_sum_(scatter)
 
 
+class PeerRows:
+    """Active-set buffers in peer-mapped memory: resampled rows are stored straight into their slot owner's buffer."""
+
+    def __init__(self, lib, device, comm: Comm, per: int, d: int):
+        import torch.distributed._symmetric_memory as symm
+
+        self.lib, self.per, self.d = lib, per, d
+        n = int(lib.tb_xrows_buffer_bytes(per, d)) // 8
+        self.buf = symm.empty(n, dtype=F64, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, torch.distributed.group.WORLD if comm.group is None else comm.group)
+        torch.cuda.synchronize()
+        torch.distributed.all_reduce(torch.zeros(1, device=device))
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=device)
+        self.x = _lib.TbXcoll()
+        self.x.rank, self.x.world, self.x.seq, self.x.cap_bytes = comm.rank, comm.world, 0, 0
+        self.x.ticket = self.ticket.data_ptr()
+        for r in range(comm.world):
+            self.x.peer[r] = int(self.handle.buffer_ptrs[r])
+
+
 def sharded_resample(core, weights: torch.Tensor, draws: Optional[torch.Tensor], systematic: bool = False,
                      u0: float = 0.0):
     """N global draws (multinomial: replicated uniforms; systematic: one uniform); returns this rank's block of
-    resampled (u, logl) rows.  Every rank searches all N draws in the global exact cdf, gathers the rows whose
-    ancestors it stores and sends each to the rank that owns the walker slot."""
+    resampled (u, logl) rows.  Every rank searches all N draws in the global exact cdf and stores the rows whose
+    ancestors it holds straight into the active-set buffer of the rank that owns the walker slot (NVLink peer
+    stores, no host synchronisation); without peer memory the rows travel by an all-to-all."""
     k, ens, comm = core.k, core.ensemble, core.comm
     n_glob = core.n_global
     d = ens.n_dim
     idx = k.ws.i64("res_idx", n_glob)
     h = k.cdf_x(weights, ens.n_total, core.generation_bounds(), ens.n_total_global, "cdf")
     k.search_x(h, draws, n_glob, idx, systematic=systematic, u0=u0)
+    core.trace["resample_idx"] = idx
+    if comm.fast is not None:
+        rows = getattr(k, "_peer_rows", None)
+        if rows is None or rows.per != core.n_local or rows.d != d:
+            rows = k._peer_rows = PeerRows(k.lib, core.device, comm, core.n_local, d)
+        rows.x.seq += 1
+        _lib.check(k.lib.tb_xrows_scatter(ptr(ens.u), ptr(ens.logl), d, ptr(idx), n_glob, core.n_local, C.byref(rows.x),
+                                          ptr(comm.fast.err), stream_ptr()), "tb_xrows_scatter")
+        off = int(k.lib.tb_xrows_offset(core.n_local, d, rows.x.seq & 1))
+        u = rows.buf[off: off + core.n_local * d].view(core.n_local, d)
+        logl = rows.buf[off + core.n_local * d: off + core.n_local * (d + 1)]
+        return u, logl
     own = torch.nonzero(idx >= 0).flatten()
     rows = torch.empty((own.numel(), d + 1), dtype=F64, device=core.device)
     if own.numel():
@@ -347,7 +483,6 @@ def sharded_resample(core, weights: torch.Tensor, draws: Optional[torch.Tensor],
         rows[:, d] = l
     lo, hi = core.slot_offset, core.slot_offset + core.n_local
     mine = exchange_owned_rows(comm, rows, own, n_glob, lo, hi)
-    core.trace["resample_idx"] = idx
     return mine[:, :d].contiguous(), mine[:, d].contiguous()
 
 

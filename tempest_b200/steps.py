@@ -330,7 +330,8 @@ class Kernels:
         return out
 
     # -- trim_weights (tools.py:10-55) ------------------------------------------------------
-    def trim(self, w: torch.Tensor, n: int, ess: float = TRIM_ESS, bins: int = TRIM_BINS, after_normalize=None):
+    def trim(self, w: torch.Tensor, n: int, ess: float = TRIM_ESS, bins: int = TRIM_BINS, after_normalize=None,
+             n_global: Optional[int] = None):
         """Normalises ``w`` IN PLACE (tools.py:36) and returns (idx int64[n_trim], w_trim[n_trim]).
 
         The reference scans i = bins-1 .. 0, each time thresholding at np.percentile(w, p_i) and
@@ -345,7 +346,7 @@ class Kernels:
         if after_normalize is not None:
             after_normalize()                 # w is final from here on (read-only below)
         h_cnt, h_s1, h_s2 = self.g_hist(w, n)
-        n_glob = self.g_int(n)
+        n_glob = int(n_global) if n_global is not None else self.g_int(n)
         ess_total = 1.0 / sumsq
         # suffix sums over binades (threshold at the lower edge of binade b keeps bins >= b)
         s1_ge = np.cumsum(h_s1[::-1])[::-1]
@@ -574,6 +575,7 @@ class Reweighter:
         ens = core.ensemble
         st.set_current("iter", st.raw("iter") + 1)
         self.probe_log = []
+        self._logz_host = None
         n = self.n_particles
         if ens.T == 0:                              # reweight.py:365-383
             st.update_current({"beta": 0.0, "logz": 0.0, "ess": self.ess_ratio * n, "cv": 0.0})
@@ -610,9 +612,13 @@ class Reweighter:
         if core.overlap:
             core.begin_cv(w)                                          # side stream; finished before the commit
             cv = None
+        elif k.sharded and not dynamic:
+            k.volume_variation_async(ens.u, w, ens.n_total, ens.n_dim)    # enqueued; read after the mutation (end_cv)
+            core._cv_sharded = True
+            cv = None
         else:
             cv = k.volume_variation(ens.u, w, ens.n_total, ens.n_dim)     # reweight.py:417-419
-        logz = float(stats[4].item())
+        logz = float(stats[4].item()) if self._logz_host is None else self._logz_host
         st.update_current({"logz": logz, "beta": float(beta), "ess": float(ess), "cv": cv})
         return w
 
@@ -648,6 +654,7 @@ class Reweighter:
             k.consume_exchanges(nprobe)              # one peer-memory exchange per probe
         if h[8] != 0.0:
             raise FloatingPointError(f"{int(h[8])} non-finite log-weights in the persistent ensemble")
+        self._logz_host = float(h[5])                  # logZ(beta) of the last probe is already on the host
         return float(h[0]), float(h[4]), res[1:7]     # (m, S1, S2, ESS, logZ, .) like tb_probe's out
 
 
@@ -668,7 +675,7 @@ class Trainer:
         st = stream_ptr()
         core._stage("train:trim")
         hook = (lambda: core.resampler.begin_async(weights)) if core.overlap else None
-        idx, wt = k.trim(weights, ens.n_total, after_normalize=hook)
+        idx, wt = k.trim(weights, ens.n_total, after_normalize=hook, n_global=ens.n_total_global)
         core._stage("train:draws")
         core.trace["trim_idx"], core.trace["trim_w"] = idx, wt
         n_trim = int(idx.numel())                       # local; equals the global count on one GPU
