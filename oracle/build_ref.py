@@ -46,6 +46,12 @@ def build(ref_root: str = "/root/reference", verbose: bool = True) -> bool:
             rel = os.path.relpath(p, dst)
             manifest[rel] = {"sha256": _sha(p), "source_sha256": _sha(os.path.join(src, rel))}
             assert manifest[rel]["sha256"] == manifest[rel]["source_sha256"], rel
+    # the reference's own unittest files ride along (tools/ref_conformance.py runs them against tempest_b200.Sampler)
+    tsrc, tdst = os.path.join(ref_root, "tests"), os.path.join(DEST, "tests")
+    if os.path.isdir(tsrc):
+        if os.path.isdir(tdst):
+            shutil.rmtree(tdst)
+        shutil.copytree(tsrc, tdst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
     with open(os.path.join(DEST, "MANIFEST.json"), "w") as f:
         json.dump({"source": src, "files": manifest}, f, indent=1, sort_keys=True)
     if verbose:

@@ -353,7 +353,9 @@ cdf_classify_kernel(CdfArgs a) {
           if (ea == eb && ea >= kMinE && ea <= 1000) E = ea;
         }
       }
-      t.E[g] = E;
+      // only the owner's entry: the other ranks' K3 kernels publish the FINAL class of their tiles into this table,
+      // possibly before this kernel gets here, and must not be overwritten with the preliminary one
+      if (w.tile_off[g] >= 0) t.E[g] = E;
     }
     run += __shfl_sync(0xffffffffu, incl, 31);
   }

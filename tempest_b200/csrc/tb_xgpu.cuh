@@ -52,11 +52,21 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Workspace of one grid-wide reduction stream (device memory, zeroed by the launcher before each launch).
 struct GridSync {
   unsigned int arrive;              // monotone ticket counter of the current launch
   unsigned int pad[3];
-  double local_xbuf[2 * kXMaxRanks * kXSlotDoubles];   // exchange buffer of single-GPU launches
+  unsigned long long bflag[2];      // local broadcast flags (sequence number of the result in bcast[parity])
+  double bcast[2][kXSlotDoubles];   // job-wide result of the current sync point, published to this GPU's CTAs
   // followed by the partial rows: double rows[2][grid][W]
   __device__ __forceinline__ double* rows() { return reinterpret_cast<double*>(this + 1); }
 };
@@ -67,7 +77,15 @@ __host__ __device__ inline size_t grid_sync_bytes(int grid, int W) {
 // Executed by ALL threads of every CTA, once per synchronisation point `k` = 0, 1, ... of this launch.
 // part[W] (shared): this CTA's partial.  On return tot[W] (shared, visible to the whole CTA) holds the job-wide
 // result.  `fold` combines rows / rank payloads in a fixed order (ColumnFold below; EssFold in tb_reweight.cu).
-// Returns 0, or 3 when a peer did not answer within the spin budget.
+//   1. every CTA publishes its row and takes a ticket (nobody waits here);
+//   2. the CTA that arrives last on this GPU folds the rows (all its threads: many loads in flight), stores the
+//      GPU's payload into slot[parity][my_rank] of EVERY rank's exchange buffer (thread r serves rank r: the NVLink
+//      stores leave in parallel) with a system-scope release of the sequence number, waits for the ranks' flags in
+//      its OWN buffer (thread r watches rank r), folds the ranks' payloads in rank order and publishes the result to
+//      the other CTAs of this GPU through a gpu-scope flag;
+//   3. every other CTA spins on that LOCAL flag only (one thread, gpu scope): no system-scope polling by thousands
+//      of threads, which delayed the very stores they were waiting for (23 us per step on 8 GPUs).
+// The flag wait is the grid barrier.  Returns 0, or 3 when a peer did not answer within the spin budget.
 template <class RowFold>
 __device__ __noinline__ int grid_xreduce(GridSync* gs, const tb_xgpu& x, int k, int W, const double* part, double* tot,
                                          RowFold fold) {
@@ -78,7 +96,6 @@ __device__ __noinline__ int grid_xreduce(GridSync* gs, const tb_xgpu& x, int k, 
   const unsigned long long seq = x.seq + (unsigned long long)k;
   const int par = (int)(seq & 1ull);
   const int world = x.world;
-  double* mybuf = (world > 1) ? x.peer[x.rank] : gs->local_xbuf;
   if (threadIdx.x < 32) {
     for (int c = lane; c < W; c += 32) __stcg(rows + (size_t)blockIdx.x * W + c, part[c]);
     __threadfence();
@@ -90,32 +107,53 @@ __device__ __noinline__ int grid_xreduce(GridSync* gs, const tb_xgpu& x, int k, 
     }
   }
   __syncthreads();
-  if (s_last) {                                           // the whole CTA folds: many loads in flight
+  if (s_last) {
     __threadfence();
     fold.rows(rows, nb, W, tot);                          // fixed order; result in tot[] (shared); ends with a CTA barrier
-    if (threadIdx.x < world) {                            // thread r serves rank r: the NVLink stores leave in parallel
-      double* dst = (world > 1) ? x.peer[threadIdx.x] : gs->local_xbuf;
-      double* slot = dst + (size_t)(par * kXMaxRanks + x.rank) * kXSlotDoubles;
-      for (int i = 0; i < W; ++i) st_relaxed_sys(slot + 1 + i, tot[i]);
-      st_release_sys(reinterpret_cast<unsigned long long*>(slot), seq);
+    if (world > 1) {
+      double* mybuf = x.peer[x.rank];
+      if ((int)threadIdx.x < world) {
+        double* slot = x.peer[threadIdx.x] + (size_t)(par * kXMaxRanks + x.rank) * kXSlotDoubles;
+        for (int i = 0; i < W; ++i) st_relaxed_sys(slot + 1 + i, tot[i]);
+        st_release_sys(reinterpret_cast<unsigned long long*>(slot), seq);
+        const unsigned long long* flag =
+            reinterpret_cast<const unsigned long long*>(mybuf + (size_t)(par * kXMaxRanks + threadIdx.x) * kXSlotDoubles);
+        if (ld_acquire_sys(flag) != seq) {
+          const unsigned long long t0 = global_ns();
+          while (ld_acquire_sys(flag) != seq) {
+            if (global_ns() - t0 > kXSpinBudgetNs) { s_bad = 1; break; }
+          }
+        }
+      }
+      __syncthreads();
+      if (!s_bad && threadIdx.x < 32) fold.ranks(mybuf + (size_t)par * kXMaxRanks * kXSlotDoubles, world, W, tot);
+      __syncthreads();
     }
+    // publish to the other CTAs of this GPU
+    if (threadIdx.x < 32) {
+      for (int c = lane; c < W; c += 32) __stcg(&gs->bcast[par][c], tot[c]);
+      if (lane == 0 && s_bad) __stcg(&gs->bcast[par][kXSlotDoubles - 1], 3.0);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_gpu(&gs->bflag[par], seq);
+    }
+    __syncthreads();
+    return s_bad ? 3 : 0;
   }
-  // wait until every rank has published sync point k (this is also the grid barrier of this GPU)
-  if (threadIdx.x < world) {
-    const unsigned long long* flag =
-        reinterpret_cast<const unsigned long long*>(mybuf + (size_t)(par * kXMaxRanks + threadIdx.x) * kXSlotDoubles);
-    if (ld_acquire_sys(flag) != seq) {
+  if (threadIdx.x == 0) {
+    if (ld_acquire_gpu(&gs->bflag[par]) != seq) {
       const unsigned long long t0 = global_ns();
-      while (ld_acquire_sys(flag) != seq) {
-        if (global_ns() - t0 > kXSpinBudgetNs) { s_bad = 1; break; }
+      while (ld_acquire_gpu(&gs->bflag[par]) != seq) {
+        if (global_ns() - t0 > 2 * kXSpinBudgetNs) { s_bad = 1; break; }
       }
     }
   }
   __syncthreads();
   if (s_bad) return 3;
-  if (threadIdx.x < 32) fold.ranks(mybuf + (size_t)par * kXMaxRanks * kXSlotDoubles, world, W, tot);
+  for (int c = threadIdx.x; c < W; c += blockDim.x) tot[c] = __ldcg(&gs->bcast[par][c]);
+  const int rc = (__ldcg(&gs->bcast[par][kXSlotDoubles - 1]) == 3.0) ? 3 : 0;
   __syncthreads();
-  return 0;
+  return rc;
 }
 
 // Column-wise fold: sum, except the columns flagged in max_cols (error codes).  Row order is fixed: thread t takes

@@ -388,7 +388,7 @@ def test_production_variates_match_numpy_restatement(env, shape):
     # a Marsaglia-Tsang comparison within 1e-5 of its threshold may resolve differently (fp32 normal inside it)
     safe = margin > 1e-5
     assert safe.mean() > 0.999
-    np.testing.assert_allclose(gd[safe], gr[safe], rtol=1e-8 if shape > 1e3 else 2e-4)
+    np.testing.assert_allclose(gd[safe], gr[safe], rtol=1e-7 if shape > 1e3 else 2e-4)   # (1 + t)^3 with a MUFU-rounded normal
     np.testing.assert_array_equal(ad[safe], ar[safe])             # the accept uniform is exact (one 32-bit word)
     assert 0.0 < ad.min() and ad.max() < 1.0
     # sharding invariance: the draws depend on the global slot only
