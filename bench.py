@@ -360,11 +360,15 @@ def main():
     calls_acc = 0
     trace = os.environ.get("BENCH_TRACE")
     marks = []
+    it_events = []                             # one event per iteration boundary (no synchronisation)
     for _ in range(args.steps):
         before = core.state.raw("calls")
         one_iteration()
         after = core.state.raw("calls")
         calls_acc += after - (before if after >= before else 0)
+        ev_it = torch.cuda.Event(enable_timing=True)
+        ev_it.record()
+        it_events.append(ev_it)
         if trace:
             marks.append(round(time.perf_counter(), 4))
     ev1.record()
@@ -373,6 +377,7 @@ def main():
     launches = _lib.launch_count - launches0
     barrier()
     ms = ev0.elapsed_time(ev1)
+    iteration_ms = [round(a.elapsed_time(b), 3) for a, b in zip([ev0] + it_events[:-1], it_events)]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -517,7 +522,7 @@ def main():
                                        "incl. the cheap warm-up and the expensive beta -> 1 iterations + posterior()",
                        "runs_completed_T": runs_T},
             "logl_evals_per_s": evals_s, "gpu_launches": None, "clocks": clock_info, "e2e": e2e,
-            "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms,
+            "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stage_ms, "iteration_ms": iteration_ms,
         }
         line["gpu_launches"] = int(launches)
         _emit(json.dumps(line))

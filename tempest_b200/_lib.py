@@ -63,6 +63,8 @@ SIGNATURES = {
     "tb_cdf_workspace_bytes": (SIZE, [c_i64]),
     "tb_cdf_exact": (c_i32, [PTR, c_i64, PTR, PTR, PTR]),
     "tb_cdf_sequential": (c_i32, [PTR, c_i64, PTR, PTR]),
+    "tb_cdf_set_chain": (None, [c_i32]),
+    "tb_cdf_chain_diag_ptr": (PTR, [PTR, c_i64]),
     "tb_cdf_tile_cap": (c_i64, [c_i64, c_i32]),
     "tb_cdf_x_workspace_bytes": (SIZE, [c_i64]),
     "tb_cdf_x_table_bytes": (SIZE, [c_i64]),

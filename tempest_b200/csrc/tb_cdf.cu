@@ -24,6 +24,7 @@
 // table memory over NVLink peer stores between the stages (one release flag per stage and rank, no host
 // involvement); every rank then runs the single-CTA stages redundantly on identical tables, so all ranks hold the
 // same exact tile-end values and the two-level search below returns numpy's global indices on any number of GPUs.
+#include <stdlib.h>
 #include "tb_common.cuh"
 #include "tb_xgpu.cuh"
 
@@ -824,6 +825,369 @@ cdf_search_x_kernel(CdfArgs a, const double* __restrict__ draws, int64_t m, doub
   }
 }
 
+
+// =================================================================================================================
+// Single-GPU path: ONE streaming kernel (read p once, write cdf once) -- a chained scan with decoupled look-back in
+// which the carried quantity is the EXACT running sum.
+//
+// A warp owns a 1024-element tile (tiles are handed out by a ticket counter, so a warp only ever waits for tiles that
+// are already running).  Per tile:
+//   1. load the tile into registers; publish its AGGREGATE: the int64 totals of inc() under two candidate binades
+//      (E, E + 1), where E is the binade of the largest exact prefix published so far (a global hint word; the running
+//      sum is monotone, so the hint is a lower bound that is almost always still the right binade).  Each 64-bit
+//      descriptor word is self-describing (binade | total), so readers never see a torn aggregate;
+//   2. look back over the predecessors' descriptors (32 per round, one per lane) to the nearest tile that has published
+//      its exact inclusive PREFIX s; the tiles in between must all offer a total under the binade of s and the integer
+//      sum must stay below 2^53 -- then s_in = (S + sum of totals) q is exactly numpy's running sum at the tile start.
+//      Anything else (a binade crossing or a tie in between, stale candidates, a tile not yet there) is retried; a tile
+//      whose candidates went stale because the hint moved on re-publishes its aggregate while it waits;
+//   3. with s_in known, the tile's own end value is published FIRST when the tile is plain (one binade, no tie), then
+//      the cdf values are produced by validated rounds: inc under the current binade -> warp scan -> first element that
+//      would reach 2^(E+1) / tie / oversized element -> literal fp64 add of that element -> next round behind it.
+// Exactness never depends on a guess: guesses only decide how early the successors can proceed.
+constexpr int kChainWarps = 8;
+constexpr int kCK = 4;                       // 128-element chunks per tile (a lane holds 4 kCK elements in registers)
+constexpr int kChainTile = 128 * kCK;
+constexpr unsigned long long kWordF = (1ull << 53) - 1ull;
+constexpr unsigned long long kCodeZero = 2046ull, kCodeInvalid = 2047ull;   // binade field of an aggregate word
+constexpr int kENone = INT32_MIN;
+
+struct ChainHead {               // 256 bytes, zeroed by cdf_chain_init_kernel
+  unsigned int ticket, pad0;
+  unsigned long long hint;       // bits of the largest exact prefix published so far
+  unsigned long long diag[6];    // 0 tiles with more than one round, 1 rounds, 2 look-back retries, 3 re-publications,
+                                 // 4 serial-regime elements, 5 late prefix publications
+};
+__host__ __device__ inline size_t chain_bytes(int64_t ntiles) { return 256 + 3 * align_up(8 * (size_t)(ntiles + 1), 256); }
+struct ChainWs {
+  ChainHead* head;
+  unsigned long long *P, *A0, *A1;
+};
+__host__ __device__ inline ChainWs chain_at(char* base, int64_t ntiles) {
+  ChainWs w;
+  const size_t stride = align_up(8 * (size_t)(ntiles + 1), 256);
+  w.head = reinterpret_cast<ChainHead*>(base);
+  w.P = reinterpret_cast<unsigned long long*>(base + 256);
+  w.A0 = reinterpret_cast<unsigned long long*>(base + 256 + stride);
+  w.A1 = reinterpret_cast<unsigned long long*>(base + 256 + 2 * stride);
+  return w;
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long word_of(int E, long long F) {
+  if (F < 0) return kCodeInvalid << 53;
+  return ((unsigned long long)(E + 1023) << 53) | (unsigned long long)F;
+}
+// total offered by an aggregate word under binade E, or -1
+__device__ __forceinline__ long long offer_of(unsigned long long w, int E) {
+  const unsigned long long code = w >> 53;
+  if (code == kCodeZero) return 0;
+  if (code == (unsigned long long)(E + 1023)) return (long long)(w & kWordF);
+  return -1;
+}
+
+__global__ void __launch_bounds__(256)
+cdf_chain_init_kernel(char* base, int64_t ntiles, int* status) {
+  const size_t words = chain_bytes(ntiles) / 8;
+  unsigned long long* w = reinterpret_cast<unsigned long long*>(base);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) w[i] = 0ull;
+  if (blockIdx.x == 0 && threadIdx.x < 16) status[threadIdx.x] = (threadIdx.x == 0) ? (int)ntiles : 0;
+}
+
+// int64 total of inc() over the tile under binade E, or -1 (an element the integer rule cannot take, or a total that
+// cannot stay inside the binade).  Warp-uniform result.
+__device__ __forceinline__ long long chain_total(const double (&v)[kCK][4], int len, int lane, int E) {
+  if (E < kMinE || E > 1000) return -1;
+  const double up = pow2(52 - E), top = pow2(E + 1);
+  long long tot = 0;
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < kCK; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = 128 * k + 4 * lane + j;
+      const long long inc = (e < len) ? inc_of(v[k][j], up, top) : 0;
+      if (inc < 0) bad = 1; else tot += inc;
+    }
+  bad = __any_sync(0xffffffffu, bad);
+  tot = (long long)warp_sum_u64((unsigned long long)tot);
+  return (bad || tot >= (1LL << 53)) ? -1 : tot;
+}
+
+// element e of the tile (warp-uniform e): the owner lane selects it from its registers, everyone receives it
+__device__ __forceinline__ double chain_element(const double (&v)[kCK][4], int lane, int e) {
+  double mine = 0.0;
+#pragma unroll
+  for (int k = 0; k < kCK; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (128 * k + 4 * lane + j == e) mine = v[k][j];
+  return __shfl_sync(0xffffffffu, mine, (e >> 2) & 31);
+}
+
+// cdf values of one tile from the exact running sum s entering it; returns the exact running sum leaving it.
+__device__ __forceinline__ double chain_emit(const double (&v)[kCK][4], int len, double s, double* __restrict__ dst, int lane,
+                                             unsigned long long* diag) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  int start = 0, rounds = 0;
+  while (start < len) {
+    if (!in_integer_regime(s)) {
+      // running sum 0 / subnormal / tiny / non-finite: literal adds, skipping stretches of zeros (s + 0 = s)
+      int cand = INT32_MAX;
+#pragma unroll
+      for (int k = 0; k < kCK; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = 128 * k + 4 * lane + j;
+          if (e >= start && e < len && !(v[k][j] == 0.0)) cand = min(cand, e);
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+      const int stop = min(cand, len);
+#pragma unroll
+      for (int k = 0; k < kCK; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int e = 128 * k + 4 * lane + j;
+          if (e >= start && e < stop) dst[e] = s;
+        }
+      if (stop < len) {
+        const double pc = chain_element(v, lane, stop);
+        s = __dadd_rn(s, pc);
+        if (lane == 0) { dst[stop] = s; atomicAdd(diag + 4, 1ull); }
+        start = stop + 1;
+      } else start = len;
+      continue;
+    }
+    ++rounds;
+    const int E = exponent_of(s);
+    const double up = pow2(52 - E), top = pow2(E + 1), q = pow2(E - 52);
+    long long carry = __double2ll_rn(s * up);                 // S: s = S q exactly
+    bool stopped = false;
+#pragma unroll
+    for (int k = 0; k < kCK; ++k) {
+      if (stopped || 128 * (k + 1) <= start || 128 * k >= len) continue;      // warp-uniform
+      const int base = 128 * k + 4 * lane;
+      long long inc[4];
+      long long run = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = base + j;
+        long long x = (e >= start && e < len) ? inc_of(v[k][j], up, top) : 0;
+        if (x < 0) x = 1LL << 53;                                // must be added literally: the prefix stops here
+        run += x;
+        inc[j] = run;
+      }
+      const long long incl = warp_incl_scan_ll(run, lane);
+      const long long before = carry + incl - run;
+      const unsigned st = __ballot_sync(0xffffffffu, before + run >= (1LL << 53));
+      if (st == 0u) {
+        double o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (double)(before + inc[j]) * q;
+        if (aligned && base >= start && base + 3 < len) {
+          reinterpret_cast<double2*>(dst + base)[0] = make_double2(o[0], o[1]);
+          reinterpret_cast<double2*>(dst + base)[1] = make_double2(o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (base + j >= start && base + j < len) dst[base + j] = o[j];
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      } else {
+        const int lc = __ffs(st) - 1;
+        int jc = 0;
+        double s_new = 0.0;
+        if (lane < lc) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (base + j >= start && base + j < len) dst[base + j] = (double)(before + inc[j]) * q;
+        } else if (lane == lc) {
+          jc = 3;
+#pragma unroll
+          for (int j = 3; j >= 0; --j) if (before + inc[j] >= (1LL << 53)) jc = j;
+          long long prev = before;
+          double pc = v[k][0];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < jc) { if (base + j >= start) dst[base + j] = (double)(before + inc[j]) * q; prev = before + inc[j]; }
+            if (j == jc) pc = v[k][j];
+          }
+          // the stop element is >= start by construction (elements before start contribute 0)
+          s_new = __dadd_rn((double)prev * q, pc);
+          dst[base + jc] = s_new;
+        }
+        s = __shfl_sync(0xffffffffu, s_new, lc);
+        start = 128 * k + 4 * lc + __shfl_sync(0xffffffffu, jc, lc) + 1;
+        stopped = true;
+      }
+    }
+    if (!stopped) { s = (double)carry * q; start = len; }
+  }
+  if (lane == 0 && rounds > 1) { atomicAdd(diag + 0, 1ull); atomicAdd(diag + 1, (unsigned long long)rounds); }
+  return s;
+}
+
+__global__ void __launch_bounds__(32 * kChainWarps, 2)
+cdf_chain_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ cdf, char* chain_base, int64_t ntiles,
+                 int* __restrict__ status) {
+  const ChainWs w = chain_at(chain_base, ntiles);
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    long long g = 0;
+    if (lane == 0) g = (long long)atomicAdd(&w.head->ticket, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= ntiles) return;
+    const int64_t off = g * (int64_t)kChainTile;
+    const int len = (int)min((int64_t)kChainTile, n - off);
+    const double* src = p + off;
+    double v[kCK][4];
+#pragma unroll
+    for (int k = 0; k < kCK; ++k) load4(src, len, 4 * (32 * k + lane), v[k]);
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < kCK; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nz = nz || !(v[k][j] == 0.0);
+    const bool allzero = !__any_sync(0xffffffffu, nz);
+
+    // ---- 1. aggregate under the candidate binades (hint, hint + 1) ------------------------------------------------
+    int Ec = kENone;                 // lower candidate binade this tile has published totals for
+    long long F0 = -1, F1 = -1;
+    auto publish = [&](int E) {
+      Ec = E;
+      F0 = chain_total(v, len, lane, E);
+      F1 = chain_total(v, len, lane, E + 1);
+      if (lane == 0) { st_relaxed_u64(w.A0 + g, word_of(E, F0)); st_relaxed_u64(w.A1 + g, word_of(E + 1, F1)); }
+    };
+    auto hint_binade = [&]() -> int {
+      unsigned long long hb = 0;
+      if (lane == 0) hb = ld_relaxed_u64(&w.head->hint);
+      hb = __shfl_sync(0xffffffffu, hb, 0);
+      const double h = __longlong_as_double((long long)hb);
+      return in_integer_regime(h) ? exponent_of(h) : kENone;
+    };
+    double s_in = 0.0;
+    if (g > 0) {
+      if (allzero) {
+        if (lane == 0) { st_relaxed_u64(w.A0 + g, kCodeZero << 53); st_relaxed_u64(w.A1 + g, kCodeZero << 53); }
+      } else {
+        const int Eh = hint_binade();
+        if (Eh != kENone) publish(Eh);
+        else if (lane == 0) { st_relaxed_u64(w.A0 + g, kCodeInvalid << 53); st_relaxed_u64(w.A1 + g, kCodeInvalid << 53); }
+      }
+      // ---- 2. look back -------------------------------------------------------------------------------------------
+      unsigned tries = 0;
+      for (;;) {
+        long long sumA = 0, sumB = 0;
+        bool okA = true, okB = true, found = false, fail = false;
+        int Ea = kENone;
+        double sP = 0.0;
+        for (long long j = g - 1; !found && !fail; j -= 32) {
+          const long long idx = j - lane;
+          unsigned long long wP = 0, a0 = 0, a1 = 0;
+          if (idx >= 0) { wP = ld_relaxed_u64(w.P + idx); a0 = ld_relaxed_u64(w.A0 + idx); a1 = ld_relaxed_u64(w.A1 + idx); }
+          const unsigned haveP = __ballot_sync(0xffffffffu, wP != 0ull);
+          const int lp = haveP ? __ffs(haveP) - 1 : 32;
+          if (lp < 32) {               // nearest exact prefix of this window (a lower bound of this tile's own start value)
+            const unsigned long long wsel = __shfl_sync(0xffffffffu, wP, lp);
+            sP = __longlong_as_double((long long)(wsel & ~(1ull << 63)));
+            found = true;
+          }
+          const bool between = lane < lp && idx >= 0;                     // tiles strictly after the prefix tile
+          if (__any_sync(0xffffffffu, between && (a0 == 0ull || a1 == 0ull))) { fail = true; break; }
+          if (lp == 32 && j - 31 <= 0) { fail = true; break; }             // reached tile 0 and it has no prefix yet
+          if (Ea == kENone) {          // binade candidates of this look-back: from the nearest tile that offers any
+            int mine = INT32_MAX;
+            if (between) {
+              const unsigned long long c0 = a0 >> 53, c1 = a1 >> 53;
+              if (c0 != kCodeZero && c0 != kCodeInvalid) mine = (int)c0 - 1023;
+              else if (c1 != kCodeZero && c1 != kCodeInvalid) mine = (int)c1 - 1023;
+            }
+            const unsigned has = __ballot_sync(0xffffffffu, mine != INT32_MAX);
+            if (has) Ea = __shfl_sync(0xffffffffu, mine, __ffs(has) - 1);
+            else if (__any_sync(0xffffffffu, between && ((a0 >> 53) == kCodeInvalid))) { fail = true; break; }
+          }
+          if (Ea != kENone) {
+            long long fa = 0, fb = 0;
+            bool ba = false, bb = false;
+            if (between) {
+              long long x = offer_of(a0, Ea); if (x < 0) x = offer_of(a1, Ea);
+              long long y = offer_of(a0, Ea + 1); if (y < 0) y = offer_of(a1, Ea + 1);
+              ba = x < 0; bb = y < 0;
+              fa = ba ? 0 : x; fb = bb ? 0 : y;
+            }
+            okA = okA && !__any_sync(0xffffffffu, ba);
+            okB = okB && !__any_sync(0xffffffffu, bb);
+            sumA += (long long)warp_sum_u64((unsigned long long)fa);
+            sumB += (long long)warp_sum_u64((unsigned long long)fb);
+            if (!okA && !okB) { fail = true; break; }
+          }
+        }
+        if (found && !fail) {
+          if (Ea == kENone) { s_in = sP; break; }                          // only all-zero tiles in between
+          if (in_integer_regime(sP)) {
+            const int E = exponent_of(sP);
+            const bool useA = (E == Ea) && okA, useB = (E == Ea + 1) && okB;
+            if (useA || useB) {
+              const long long S0 = __double2ll_rn(sP * pow2(52 - E));
+              const long long tot = S0 + (useA ? sumA : sumB);
+              if (tot < (1LL << 53)) { s_in = (double)tot * pow2(E - 52); break; }
+            }
+          }
+        }
+        // not yet.  If a predecessor's exact prefix is already two binades past this tile's candidates (or it had none),
+        // re-publish the aggregate under that prefix's binade: a lower bound of the binade this tile starts in.
+        if (!allzero && found && in_integer_regime(sP)) {
+          const int Es = exponent_of(sP);
+          if (Ec == kENone || Es > Ec + 1) {
+            publish(Es);
+            if (lane == 0) atomicAdd(w.head->diag + 3, 1ull);
+          }
+        }
+        ++tries;
+        if (tries > 8000000u) {        // ~1 s of polling: a predecessor never published (cannot happen; never hang the GPU)
+          if (lane == 0) status[4] = 7;
+          s_in = __longlong_as_double(0x7ff8000000000000LL);
+          break;
+        }
+        __nanosleep(tries < 8 ? 20 : 100);
+      }
+      if (tries && lane == 0) atomicAdd(w.head->diag + 2, (unsigned long long)tries);
+    }
+    // ---- 3. own end value first (plain tiles), then the cdf values -------------------------------------------------
+    bool published = false;
+    double s_out = s_in;
+    if (allzero) published = true;
+    else if (in_integer_regime(s_in)) {
+      const int E = exponent_of(s_in);
+      const long long F = (E == Ec) ? F0 : ((Ec != kENone && E == Ec + 1) ? F1 : chain_total(v, len, lane, E));
+      if (F >= 0) {
+        const long long tot = __double2ll_rn(s_in * pow2(52 - E)) + F;
+        if (tot < (1LL << 53)) { s_out = (double)tot * pow2(E - 52); published = true; }
+      }
+    }
+    auto publish_prefix = [&](double s) {
+      if (lane == 0) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s) & ~(1ull << 63);
+        st_relaxed_u64(w.P + g, bits | (1ull << 63));
+        atomicMax(&w.head->hint, bits);
+      }
+    };
+    if (published) publish_prefix(s_out);
+    const double s_end = chain_emit(v, len, s_in, cdf + off, lane, w.head->diag);
+    if (!published) {
+      publish_prefix(s_end);
+      if (lane == 0) atomicAdd(w.head->diag + 5, 1ull);
+    }
+  }
+}
+
 __global__ void cdf_set_bounds_kernel(int64_t* seg, int64_t n) { seg[0] = 0; seg[1] = n; }
 
 CdfArgs make_args(const double* p, int64_t n_local, double* cdf, void* workspace, int64_t ntg_cap, const tb_cdf_x* x) {
@@ -851,10 +1215,23 @@ int64_t tb_cdf_tile_cap(int64_t n_global, int32_t n_segments) {
 }
 size_t tb_cdf_x_workspace_bytes(int64_t ntg_cap) { return local_bytes(ntg_cap) + x_layout(ntg_cap).total + 256; }
 size_t tb_cdf_x_table_bytes(int64_t ntg_cap) { return 2 * x_layout(ntg_cap).total; }
-size_t tb_cdf_workspace_bytes(int64_t n) { return tb_cdf_x_workspace_bytes(tb_cdf_tile_cap(n, 1)); }
+// single-GPU workspace: the multi-kernel pipeline's scratch followed by the descriptors of the chained kernel
+size_t tb_cdf_workspace_bytes(int64_t n) {
+  const int64_t cap = tb_cdf_tile_cap(n, 1);
+  return align_up(tb_cdf_x_workspace_bytes(cap), 256) + chain_bytes((n + kChainTile - 1) / kChainTile + 1);
+}
+static int g_cdf_chain = -1;     // 1: chained single-pass kernel (default), 0: multi-kernel pipeline (TB_CDF_CHAIN=0)
+void tb_cdf_set_chain(int32_t on) { g_cdf_chain = on ? 1 : 0; }
 
 // status of the last call on this workspace: {tiles, segments, runs, hard tiles, error, ...} (device ints)
 int32_t* tb_cdf_status_ptr(void* workspace) { return reinterpret_cast<int32_t*>(workspace); }
+// diagnostics of the chained kernel's last call on this workspace (device words: multi-round tiles, rounds, look-back
+// retries, re-publications, serial-regime elements, late prefix publications)
+uint64_t* tb_cdf_chain_diag_ptr(void* workspace, int64_t n) {
+  const int64_t cap = tb_cdf_tile_cap(n, 1);
+  char* chain = reinterpret_cast<char*>(workspace) + align_up(tb_cdf_x_workspace_bytes(cap), 256);
+  return reinterpret_cast<uint64_t*>(reinterpret_cast<ChainHead*>(chain)->diag);
+}
 double* tb_cdf_total_ptr(void* workspace, int64_t ntg_cap) { return local_at(reinterpret_cast<char*>(workspace), ntg_cap).total; }
 
 int tb_cdf_exact_x(const double* p, int64_t n_local, const int64_t* seg_begin, int32_t n_gen, int64_t n_global,
@@ -898,8 +1275,32 @@ int tb_cdf_exact_x(const double* p, int64_t n_local, const int64_t* seg_begin, i
 
 int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_stream_t stream) {
   if (n <= 0 || !p || !cdf || !workspace) return TB_ERR_ARG;
-  // single segment [0, n): the bounds live at the end of the workspace (written on the stream)
   const int64_t cap = tb_cdf_tile_cap(n, 1);
+  if (g_cdf_chain < 0) {
+    const char* e = getenv("TB_CDF_CHAIN");
+    g_cdf_chain = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (g_cdf_chain) {
+    cudaStream_t st = as_stream(stream);
+    const int64_t ntiles = (n + kChainTile - 1) / kChainTile;
+    char* chain = reinterpret_cast<char*>(workspace) + align_up(tb_cdf_x_workspace_bytes(cap), 256);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cdf_chain_kernel, 32 * kChainWarps, 0);
+      if (e != cudaSuccess) return (int)e;
+      if (per_sm < 1) per_sm = 1;
+    }
+    const size_t words = chain_bytes(ntiles) / 8;
+    int igrid = (int)((words + 256 * 8 - 1) / (256 * 8));
+    if (igrid > sm_count() * 4) igrid = sm_count() * 4;
+    cdf_chain_init_kernel<<<igrid < 1 ? 1 : igrid, 256, 0, st>>>(chain, ntiles, reinterpret_cast<int*>(workspace));
+    int64_t grid = (ntiles + kChainWarps - 1) / kChainWarps;
+    if (grid > (int64_t)per_sm * sm_count()) grid = (int64_t)per_sm * sm_count();
+    cdf_chain_kernel<<<(unsigned)grid, 32 * kChainWarps, 0, st>>>(p, n, cdf, chain, ntiles, reinterpret_cast<int*>(workspace));
+    TB_CHECK_LAUNCH();
+    return TB_OK;
+  }
+  // single segment [0, n): the bounds live at the end of the workspace (written on the stream)
   int64_t* seg = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(workspace) + local_bytes(cap) + x_layout(cap).total);
   cdf_set_bounds_kernel<<<1, 1, 0, as_stream(stream)>>>(seg, n);
   return tb_cdf_exact_x(p, n, seg, 1, n, cap, cdf, workspace, nullptr, stream);

@@ -150,6 +150,74 @@ def test_cdf_exact_is_bitwise_numpy_cumsum(env, kind, n):
         f"first mismatch at {np.nonzero(got != ref)[0][:3]}"
 
 
+def _cdf_bitwise(env, p, name="t_cdf"):
+    ref = np.cumsum(p)
+    got = env.k.cdf(dev_arr(env, p), len(p), name).cpu().numpy()
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), \
+        f"first mismatch at {np.nonzero(got.view(np.uint64) != ref.view(np.uint64))[0][:3]} of {len(p)}"
+
+
+@pytest.mark.parametrize("chain", [1, 0])
+def test_cdf_exact_hard_cases_both_paths(env, chain):
+    """Round-half ties, oversized elements, binade crossings on tile boundaries, long zero / subnormal stretches and a
+    PS-shaped vector (generations of rising weight), through the chained single-pass kernel (chain = 1, the default
+    single-GPU path) and the multi-kernel pipeline (chain = 0, the path sharded runs use)."""
+    env.lib.tb_cdf_set_chain(chain)
+    try:
+        rng = np.random.default_rng(77)
+        cases = []
+        # exact ties: s = 1, then elements of exactly half an ulp (round-half-even decides), mixed with ordinary ones
+        t = np.full(5000, 2.0 ** -53)
+        t[0] = 1.0
+        t[rng.integers(1, 5000, 200)] = rng.random(200) * 1e-9
+        cases.append(t)
+        # every element dominates the running sum (each add crosses at least one binade)
+        cases.append(3.0 ** np.arange(600) * 1e-200)
+        # a crossing exactly at the tile boundaries of both kernels (512 / 1024 elements)
+        b = np.full(4096, 2.0 ** -13)
+        cases.append(b)                                   # sum hits powers of two at indices 2^k - 1
+        # leading zeros over many tiles, then subnormals, then ordinary weights
+        z = np.zeros(70000)
+        z[30000:30500] = 5e-324 * rng.integers(1, 1000, 500)
+        z[40000:] = rng.random(30000) * 1e-3
+        z[50000] = 0.7
+        cases.append(z)
+        # tiny normal range (below the integer regime), slowly growing into it
+        cases.append(np.exp(rng.uniform(-700.0, -640.0, 20000)))
+        # PS-shaped: 24 generations of 8192, log-weights rising by ~12 per generation with heavy scatter, early ones 0
+        g = np.concatenate([np.exp(np.minimum(0.0, -300.0 + 12.5 * t_ + 6.0 * rng.standard_normal(8192))) for t_ in range(24)])
+        g[: 3 * 8192] = 0.0
+        cases.append(g / g.sum())
+        # large: 2^22 skewed (many tiles in flight behind the few crossings)
+        big = np.exp(-0.5 * rng.chisquare(10, 1 << 22) * 30.0)
+        cases.append(big / big.sum())
+        for c in cases:
+            _cdf_bitwise(env, c)
+    finally:
+        env.lib.tb_cdf_set_chain(1)
+
+
+def test_cdf_exact_chain_large_and_real_weights(env):
+    """2^25 elements, and the weight vector of a finished PS run at beta = 1 (the vector the resampling step sees)."""
+    import tempest_b200 as tp
+
+    rng = np.random.default_rng(78)
+    p = rng.random(1 << 25) ** 8
+    p /= p.sum()
+    _cdf_bitwise(env, p, "t_cdf_big")
+    s = tp.Sampler(tp.UniformPrior(-10.0, 10.0, 10), tp.Rosenbrock(10), 10, n_particles=1 << 15, vectorize=True,
+                   clustering=False, random_state=3)
+    s.run(progress=False)
+    core = s._core
+    ens, k = core.ensemble, core.k
+    k.probe(ens, 1.0)
+    w = k.weights(ens, 1.0, k.probe_out, core.weights_buffer())
+    k.g_normalize(w, ens.n_total)
+    wh = w.cpu().numpy().copy()
+    got = k.cdf(w, ens.n_total, "t_cdf_real").cpu().numpy()
+    assert np.array_equal(got.view(np.uint64), np.cumsum(wh).view(np.uint64))
+
+
 def test_cdf_sequential_kernel_agrees(env):
     rng = np.random.default_rng(9)
     n = 50000
