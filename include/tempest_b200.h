@@ -96,8 +96,9 @@ int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_st
 /* tb_cdf_exact runs ONE streaming kernel on a single GPU (chained scan with decoupled look-back that carries the exact
  * running sum; reads p once, writes cdf once).  tb_cdf_set_chain(0) selects the multi-kernel pipeline of
  * tb_cdf_exact_x instead (A/B; also the environment variable TB_CDF_CHAIN=0).  tb_cdf_chain_diag_ptr: device
- * uint64[6] of the last chained call on `workspace` {tiles needing > 1 round, rounds in them, look-back retries,
- * re-published aggregates, serial-regime elements, late prefix publications}. */
+ * uint64[24] of the last chained call on `workspace` {tiles needing > 1 round, rounds in them, look-back retries,
+ * re-published aggregates, serial-regime elements, late prefix publications, look-back rounds, ns summed over tiles
+ * ticket -> aggregate, aggregate -> start value, start value -> done, ...}. */
 void tb_cdf_set_chain(int32_t on);
 uint64_t* tb_cdf_chain_diag_ptr(void* workspace, int64_t n);
 /* The same over a SHARDED weight vector.  The global order is generation-major, rank-minor (the order of the

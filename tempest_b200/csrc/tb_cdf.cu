@@ -847,7 +847,8 @@ cdf_search_x_kernel(CdfArgs a, const double* __restrict__ draws, int64_t m, doub
 // Exactness never depends on a guess: guesses only decide how early the successors can proceed.
 constexpr int kChainWarps = 8;
 constexpr int kCK = 4;                       // 128-element chunks per tile (a lane holds 4 kCK elements in registers)
-constexpr int kChainTile = 128 * kCK;
+constexpr int kWarpTile = 128 * kCK;          // elements per warp
+constexpr int kChainTile = kWarpTile * kChainWarps;   // elements per CTA tile (one descriptor)
 constexpr unsigned long long kWordF = (1ull << 53) - 1ull;
 constexpr unsigned long long kCodeZero = 2046ull, kCodeInvalid = 2047ull;   // binade field of an aggregate word
 constexpr int kENone = INT32_MIN;
@@ -855,8 +856,9 @@ constexpr int kENone = INT32_MIN;
 struct ChainHead {               // 256 bytes, zeroed by cdf_chain_init_kernel
   unsigned int ticket, pad0;
   unsigned long long hint;       // bits of the largest exact prefix published so far
-  unsigned long long diag[6];    // 0 tiles with more than one round, 1 rounds, 2 look-back retries, 3 re-publications,
-                                 // 4 serial-regime elements, 5 late prefix publications
+  unsigned long long diag[24];   // 0 tiles with more than one round, 1 rounds, 2 look-back retries, 3 re-publications,
+                                 // 4 serial-regime elements, 5 late prefix publications, 6 look-back windows read,
+                                 // 7 / 8 / 9 ns summed over tiles: ticket -> aggregate, aggregate -> start value, start -> done
 };
 __host__ __device__ inline size_t chain_bytes(int64_t ntiles) { return 256 + 3 * align_up(8 * (size_t)(ntiles + 1), 256); }
 struct ChainWs {
@@ -1033,18 +1035,113 @@ __device__ __forceinline__ double chain_emit(const double (&v)[kCK][4], int len,
   return s;
 }
 
+// One look-back attempt by a single warp over the CTA-tile descriptors before tile g.  Returns 1 with the exact start
+// value in s_in; 0 when it has to be retried, with found / sP = the nearest exact prefix it saw (a lower bound of the
+// tile's own start value, used to refresh stale candidates).
+__device__ __forceinline__ int chain_look_back(const ChainWs& w, long long g, int lane, double& s_in, bool& found, double& sP,
+                                               unsigned& nwin) {
+  long long sumA = 0, sumB = 0;
+  bool okA = true, okB = true, fail = false;
+  int why = 14;
+  int Ea = kENone;
+  found = false;
+  sP = 0.0;
+  // two windows of 32 predecessors per L2 round trip (the chain of exact prefixes advances one round trip per window)
+  for (long long j0 = g - 1; !found && !fail; j0 -= 64) {
+    unsigned long long wPs[2] = {0ull, 0ull}, a0s[2] = {0ull, 0ull}, a1s[2] = {0ull, 0ull};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long idx = j0 - 32 * h - lane;
+      if (idx >= 0) { wPs[h] = ld_relaxed_u64(w.P + idx); a0s[h] = ld_relaxed_u64(w.A0 + idx); a1s[h] = ld_relaxed_u64(w.A1 + idx); }
+    }
+    ++nwin;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (found || fail) break;
+      const long long j = j0 - 32 * h;
+      if (j < 0) { fail = true; why = 14; break; }
+      const long long idx = j - lane;
+      const unsigned long long wP = wPs[h], a0 = a0s[h], a1 = a1s[h];
+      const unsigned haveP = __ballot_sync(0xffffffffu, wP != 0ull);
+      const int lp = haveP ? __ffs(haveP) - 1 : 32;
+      if (lp < 32) {
+        const unsigned long long wsel = __shfl_sync(0xffffffffu, wP, lp);
+        sP = __longlong_as_double((long long)(wsel & ~(1ull << 63)));
+        found = true;
+      }
+      const bool between = lane < lp && idx >= 0;                     // tiles strictly after the prefix tile
+      if (__any_sync(0xffffffffu, between && (a0 == 0ull || a1 == 0ull))) { fail = true; why = 10; break; }
+      if (lp == 32 && j - 31 <= 0) { fail = true; why = 11; break; }             // reached tile 0 and it has no prefix yet
+      if (Ea == kENone) {          // binade candidates of this look-back: from the nearest tile that offers any
+        int mine = INT32_MAX;
+        if (between) {
+          const unsigned long long c0 = a0 >> 53, c1 = a1 >> 53;
+          if (c0 != kCodeZero && c0 != kCodeInvalid) mine = (int)c0 - 1023;
+          else if (c1 != kCodeZero && c1 != kCodeInvalid) mine = (int)c1 - 1023;
+        }
+        const unsigned has = __ballot_sync(0xffffffffu, mine != INT32_MAX);
+        if (has) Ea = __shfl_sync(0xffffffffu, mine, __ffs(has) - 1);
+        else if (__any_sync(0xffffffffu, between && ((a0 >> 53) == kCodeInvalid))) { fail = true; why = 12; break; }
+      }
+      if (Ea != kENone) {
+        long long fa = 0, fb = 0;
+        bool ba = false, bb = false;
+        if (between) {
+          long long x = offer_of(a0, Ea); if (x < 0) x = offer_of(a1, Ea);
+          long long y = offer_of(a0, Ea + 1); if (y < 0) y = offer_of(a1, Ea + 1);
+          ba = x < 0; bb = y < 0;
+          fa = ba ? 0 : x; fb = bb ? 0 : y;
+        }
+        okA = okA && !__any_sync(0xffffffffu, ba);
+        okB = okB && !__any_sync(0xffffffffu, bb);
+        sumA += (long long)warp_sum_u64((unsigned long long)fa);
+        sumB += (long long)warp_sum_u64((unsigned long long)fb);
+        if (!okA && !okB) { fail = true; why = 13; break; }
+      }
+    }
+  }
+  if (!found || fail) { if (lane == 0) atomicAdd(w.head->diag + why, 1ull); return 0; }
+  if (Ea == kENone) { s_in = sP; return 1; }                          // only all-zero tiles in between
+  if (!in_integer_regime(sP)) { if (lane == 0) atomicAdd(w.head->diag + 15, 1ull); return 0; }
+  const int E = exponent_of(sP);
+  const bool useA = (E == Ea) && okA, useB = (E == Ea + 1) && okB;
+  if (!useA && !useB) { if (lane == 0) atomicAdd(w.head->diag + 16, 1ull); return 0; }
+  const long long tot = __double2ll_rn(sP * pow2(52 - E)) + (useA ? sumA : sumB);
+  if (tot >= (1LL << 53)) { if (lane == 0) atomicAdd(w.head->diag + 17, 1ull); return 0; }
+  s_in = (double)tot * pow2(E - 52);
+  return 1;
+}
+
+struct ChainShared {
+  long long g;
+  unsigned long long hint;
+  long long F0[kChainWarps], F1[kChainWarps];   // per-warp totals under the candidate binades (Ec, Ec + 1); -1: none
+  long long FE[kChainWarps];                    // per-warp totals under the binade of the tile's exact start value
+  int zero[kChainWarps];                        // warp's part of the tile is all zeros (or empty)
+  double s_in;
+  int cmd, cmd_E;                               // outcome of warp 0's look-back: 1 done, 2 re-publish under cmd_E, 3 timeout
+  volatile double hand[kChainWarps + 1];        // exact start value handed from warp to warp when it cannot be computed
+  volatile int hand_ready[kChainWarps + 1];     //   in parallel (a crossing / tie inside the CTA tile)
+};
+
 __global__ void __launch_bounds__(32 * kChainWarps, 2)
 cdf_chain_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ cdf, char* chain_base, int64_t ntiles,
                  int* __restrict__ status) {
+  __shared__ ChainShared sm;
   const ChainWs w = chain_at(chain_base, ntiles);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (;;) {
-    long long g = 0;
-    if (lane == 0) g = (long long)atomicAdd(&w.head->ticket, 1u);
-    g = __shfl_sync(0xffffffffu, g, 0);
+    __syncthreads();                                     // the previous tile's shared state is no longer in use
+    if (threadIdx.x == 0) {
+      sm.g = (long long)atomicAdd(&w.head->ticket, 1u);
+      sm.hint = ld_relaxed_u64(&w.head->hint);
+    }
+    __syncthreads();
+    const long long g = sm.g;
     if (g >= ntiles) return;
-    const int64_t off = g * (int64_t)kChainTile;
-    const int len = (int)min((int64_t)kChainTile, n - off);
+    const unsigned long long t_ticket = global_ns();
+    const int64_t off = g * (int64_t)kChainTile + (int64_t)wid * kWarpTile;      // this warp's part of the CTA tile
+    const int len = (int)max((int64_t)0, min((int64_t)kWarpTile, n - off));
     const double* src = p + off;
     double v[kCK][4];
 #pragma unroll
@@ -1054,137 +1151,160 @@ cdf_chain_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ c
     for (int k = 0; k < kCK; ++k)
 #pragma unroll
       for (int j = 0; j < 4; ++j) nz = nz || !(v[k][j] == 0.0);
-    const bool allzero = !__any_sync(0xffffffffu, nz);
+    const bool wzero = !__any_sync(0xffffffffu, nz);
 
-    // ---- 1. aggregate under the candidate binades (hint, hint + 1) ------------------------------------------------
-    int Ec = kENone;                 // lower candidate binade this tile has published totals for
-    long long F0 = -1, F1 = -1;
-    auto publish = [&](int E) {
+    int Ec = kENone;                 // lower candidate binade the tile's aggregate is published under (CTA-uniform)
+    long long F0 = -1, F1 = -1;      // this warp's totals under (Ec, Ec + 1)
+    auto totals = [&](int E) {       // all warps: candidate totals -> shared
       Ec = E;
-      F0 = chain_total(v, len, lane, E);
-      F1 = chain_total(v, len, lane, E + 1);
-      if (lane == 0) { st_relaxed_u64(w.A0 + g, word_of(E, F0)); st_relaxed_u64(w.A1 + g, word_of(E + 1, F1)); }
+      F0 = wzero ? 0 : chain_total(v, len, lane, E);
+      F1 = wzero ? 0 : chain_total(v, len, lane, E + 1);
+      if (lane == 0) { sm.F0[wid] = F0; sm.F1[wid] = F1; }
     };
-    auto hint_binade = [&]() -> int {
-      unsigned long long hb = 0;
-      if (lane == 0) hb = ld_relaxed_u64(&w.head->hint);
-      hb = __shfl_sync(0xffffffffu, hb, 0);
-      const double h = __longlong_as_double((long long)hb);
-      return in_integer_regime(h) ? exponent_of(h) : kENone;
+    auto publish_aggregate = [&]() { // warp 0, after a barrier
+      bool allz = true;
+      long long t0 = 0, t1 = 0;
+      for (int i = 0; i < kChainWarps; ++i) {
+        allz = allz && sm.zero[i] != 0;
+        if (Ec != kENone) {
+          const long long a = sm.F0[i], b = sm.F1[i];
+          t0 = (t0 < 0 || a < 0) ? -1 : t0 + a;
+          t1 = (t1 < 0 || b < 0) ? -1 : t1 + b;
+        }
+      }
+      if (lane == 0) {
+        unsigned long long w0 = kCodeInvalid << 53, w1 = kCodeInvalid << 53;
+        if (allz) { w0 = kCodeZero << 53; w1 = kCodeZero << 53; }
+        else if (Ec != kENone) {
+          w0 = word_of(Ec, (t0 >= 0 && t0 < (1LL << 53)) ? t0 : -1);
+          w1 = word_of(Ec + 1, (t1 >= 0 && t1 < (1LL << 53)) ? t1 : -1);
+        }
+        st_relaxed_u64(w.A0 + g, w0);
+        st_relaxed_u64(w.A1 + g, w1);
+      }
     };
     double s_in = 0.0;
+    if (lane == 0) sm.zero[wid] = wzero ? 1 : 0;
     if (g > 0) {
-      if (allzero) {
-        if (lane == 0) { st_relaxed_u64(w.A0 + g, kCodeZero << 53); st_relaxed_u64(w.A1 + g, kCodeZero << 53); }
-      } else {
-        const int Eh = hint_binade();
-        if (Eh != kENone) publish(Eh);
-        else if (lane == 0) { st_relaxed_u64(w.A0 + g, kCodeInvalid << 53); st_relaxed_u64(w.A1 + g, kCodeInvalid << 53); }
+      // ---- 1. aggregate under the candidate binades (hint, hint + 1) ----------------------------------------------
+      {
+        const double h = __longlong_as_double((long long)sm.hint);
+        if (in_integer_regime(h)) totals(exponent_of(h));
       }
-      // ---- 2. look back -------------------------------------------------------------------------------------------
-      unsigned tries = 0;
+      __syncthreads();
+      const unsigned long long t_agg = global_ns();
+      // ---- 2. look back (warp 0); the other warps wait at the barrier ----------------------------------------------
       for (;;) {
-        long long sumA = 0, sumB = 0;
-        bool okA = true, okB = true, found = false, fail = false;
-        int Ea = kENone;
-        double sP = 0.0;
-        for (long long j = g - 1; !found && !fail; j -= 32) {
-          const long long idx = j - lane;
-          unsigned long long wP = 0, a0 = 0, a1 = 0;
-          if (idx >= 0) { wP = ld_relaxed_u64(w.P + idx); a0 = ld_relaxed_u64(w.A0 + idx); a1 = ld_relaxed_u64(w.A1 + idx); }
-          const unsigned haveP = __ballot_sync(0xffffffffu, wP != 0ull);
-          const int lp = haveP ? __ffs(haveP) - 1 : 32;
-          if (lp < 32) {               // nearest exact prefix of this window (a lower bound of this tile's own start value)
-            const unsigned long long wsel = __shfl_sync(0xffffffffu, wP, lp);
-            sP = __longlong_as_double((long long)(wsel & ~(1ull << 63)));
-            found = true;
-          }
-          const bool between = lane < lp && idx >= 0;                     // tiles strictly after the prefix tile
-          if (__any_sync(0xffffffffu, between && (a0 == 0ull || a1 == 0ull))) { fail = true; break; }
-          if (lp == 32 && j - 31 <= 0) { fail = true; break; }             // reached tile 0 and it has no prefix yet
-          if (Ea == kENone) {          // binade candidates of this look-back: from the nearest tile that offers any
-            int mine = INT32_MAX;
-            if (between) {
-              const unsigned long long c0 = a0 >> 53, c1 = a1 >> 53;
-              if (c0 != kCodeZero && c0 != kCodeInvalid) mine = (int)c0 - 1023;
-              else if (c1 != kCodeZero && c1 != kCodeInvalid) mine = (int)c1 - 1023;
+        if (wid == 0) {
+          publish_aggregate();
+          unsigned tries = 0, nwin = 0;
+          int cmd = 0, cmd_E = 0;
+          double s_found = 0.0;
+          while (cmd == 0) {
+            bool found; double sP;
+            if (chain_look_back(w, g, lane, s_found, found, sP, nwin)) { cmd = 1; break; }
+            // stale or missing candidates?  An INVALID tile cannot have been passed by a successor, so the global hint is
+            // still a lower bound of its start value; otherwise only a predecessor's exact prefix is.
+            int En = kENone;
+            if (Ec == kENone) {
+              unsigned long long hb = 0;
+              if (lane == 0) hb = ld_relaxed_u64(&w.head->hint);
+              hb = __shfl_sync(0xffffffffu, hb, 0);
+              const double h = __longlong_as_double((long long)hb);
+              if (in_integer_regime(h)) En = exponent_of(h);
             }
-            const unsigned has = __ballot_sync(0xffffffffu, mine != INT32_MAX);
-            if (has) Ea = __shfl_sync(0xffffffffu, mine, __ffs(has) - 1);
-            else if (__any_sync(0xffffffffu, between && ((a0 >> 53) == kCodeInvalid))) { fail = true; break; }
-          }
-          if (Ea != kENone) {
-            long long fa = 0, fb = 0;
-            bool ba = false, bb = false;
-            if (between) {
-              long long x = offer_of(a0, Ea); if (x < 0) x = offer_of(a1, Ea);
-              long long y = offer_of(a0, Ea + 1); if (y < 0) y = offer_of(a1, Ea + 1);
-              ba = x < 0; bb = y < 0;
-              fa = ba ? 0 : x; fb = bb ? 0 : y;
+            if (found && in_integer_regime(sP)) {
+              const int Es = exponent_of(sP);
+              if (Ec == kENone || Es > Ec + 1) En = (En == kENone || Es > En) ? Es : En;
             }
-            okA = okA && !__any_sync(0xffffffffu, ba);
-            okB = okB && !__any_sync(0xffffffffu, bb);
-            sumA += (long long)warp_sum_u64((unsigned long long)fa);
-            sumB += (long long)warp_sum_u64((unsigned long long)fb);
-            if (!okA && !okB) { fail = true; break; }
+            bool allz = true;
+            for (int i = 0; i < kChainWarps; ++i) allz = allz && sm.zero[i] != 0;
+            if (En != kENone && !allz) { cmd = 2; cmd_E = En; break; }
+            ++tries;
+            if (tries > 8000000u) { cmd = 3; break; }      // a predecessor never published (cannot happen; never hang)
+            __nanosleep(tries < 64 ? 20 : 100);
+          }
+          if (lane == 0) {
+            sm.cmd = cmd; sm.cmd_E = cmd_E; sm.s_in = s_found;
+            if (tries) atomicAdd(w.head->diag + 2, (unsigned long long)tries);
+            atomicAdd(w.head->diag + 6, (unsigned long long)nwin);
+            if (cmd == 2) atomicAdd(w.head->diag + 3, 1ull);
+            if (cmd == 3) { status[4] = 7; sm.s_in = __longlong_as_double(0x7ff8000000000000LL); }
           }
         }
-        if (found && !fail) {
-          if (Ea == kENone) { s_in = sP; break; }                          // only all-zero tiles in between
-          if (in_integer_regime(sP)) {
-            const int E = exponent_of(sP);
-            const bool useA = (E == Ea) && okA, useB = (E == Ea + 1) && okB;
-            if (useA || useB) {
-              const long long S0 = __double2ll_rn(sP * pow2(52 - E));
-              const long long tot = S0 + (useA ? sumA : sumB);
-              if (tot < (1LL << 53)) { s_in = (double)tot * pow2(E - 52); break; }
-            }
-          }
-        }
-        // not yet.  If a predecessor's exact prefix is already two binades past this tile's candidates (or it had none),
-        // re-publish the aggregate under that prefix's binade: a lower bound of the binade this tile starts in.
-        if (!allzero && found && in_integer_regime(sP)) {
-          const int Es = exponent_of(sP);
-          if (Ec == kENone || Es > Ec + 1) {
-            publish(Es);
-            if (lane == 0) atomicAdd(w.head->diag + 3, 1ull);
-          }
-        }
-        ++tries;
-        if (tries > 8000000u) {        // ~1 s of polling: a predecessor never published (cannot happen; never hang the GPU)
-          if (lane == 0) status[4] = 7;
-          s_in = __longlong_as_double(0x7ff8000000000000LL);
-          break;
-        }
-        __nanosleep(tries < 8 ? 20 : 100);
+        __syncthreads();
+        if (sm.cmd != 2) break;
+        totals(sm.cmd_E);
+        __syncthreads();
       }
-      if (tries && lane == 0) atomicAdd(w.head->diag + 2, (unsigned long long)tries);
-    }
-    // ---- 3. own end value first (plain tiles), then the cdf values -------------------------------------------------
-    bool published = false;
-    double s_out = s_in;
-    if (allzero) published = true;
-    else if (in_integer_regime(s_in)) {
-      const int E = exponent_of(s_in);
-      const long long F = (E == Ec) ? F0 : ((Ec != kENone && E == Ec + 1) ? F1 : chain_total(v, len, lane, E));
-      if (F >= 0) {
-        const long long tot = __double2ll_rn(s_in * pow2(52 - E)) + F;
-        if (tot < (1LL << 53)) { s_out = (double)tot * pow2(E - 52); published = true; }
+      s_in = sm.s_in;
+      if (threadIdx.x == 0) {
+        const unsigned long long t_in = global_ns();
+        atomicAdd(w.head->diag + 7, t_agg - t_ticket);
+        atomicAdd(w.head->diag + 8, t_in - t_agg);
+        sm.hint = t_in;                 // (slot reused: start-of-emit time of this tile)
       }
     }
-    auto publish_prefix = [&](double s) {
+    // ---- 3. per-warp exact start values, the tile's end value first when it is plain, then the cdf values ------------
+    const bool reg_in = in_integer_regime(s_in);
+    const int E = reg_in ? exponent_of(s_in) : kENone;
+    {
+      long long FE = -1;
+      if (wzero) FE = 0;
+      else if (reg_in) FE = (E == Ec) ? F0 : ((Ec != kENone && E == Ec + 1) ? F1 : chain_total(v, len, lane, E));
+      if (lane == 0) { sm.FE[wid] = FE; sm.hand_ready[wid + 1] = 0; }
+    }
+    __syncthreads();
+    // start value of this warp: s_in carried through the preceding warps' totals while everything stays plain
+    bool known = true;
+    long long S = reg_in ? __double2ll_rn(s_in * pow2(52 - E)) : 0;
+    for (int i = 0; i < wid && known; ++i) {
+      if (sm.zero[i]) continue;
+      const long long f = sm.FE[i];
+      if (!reg_in || f < 0 || S + f >= (1LL << 53)) known = false; else S += f;
+    }
+    double s_start;
+    if (known) s_start = reg_in ? (double)S * pow2(E - 52) : s_in;
+    else {
+      if (lane == 0) { while (sm.hand_ready[wid] == 0) __nanosleep(20); }
+      __syncwarp();
+      s_start = sm.hand[wid];
+    }
+    // end value without walking the elements?
+    bool early = false;
+    double s_end = s_start;
+    if (wzero) early = true;
+    else if (in_integer_regime(s_start)) {
+      const int Es = exponent_of(s_start);
+      const long long f = (Es == E) ? sm.FE[wid] : chain_total(v, len, lane, Es);
+      if (f >= 0) {
+        const long long tot = __double2ll_rn(s_start * pow2(52 - Es)) + f;
+        if (tot < (1LL << 53)) { s_end = (double)tot * pow2(Es - 52); early = true; }
+      }
+    }
+    auto hand_on = [&](double s) {
       if (lane == 0) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(s) & ~(1ull << 63);
-        st_relaxed_u64(w.P + g, bits | (1ull << 63));
-        atomicMax(&w.head->hint, bits);
+        if (wid + 1 < kChainWarps) {
+          sm.hand[wid + 1] = s;
+          __threadfence_block();
+          sm.hand_ready[wid + 1] = 1;
+        } else {               // last warp: the CTA tile's exact inclusive prefix
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(s) & ~(1ull << 63);
+          st_relaxed_u64(w.P + g, bits | (1ull << 63));
+          atomicMax(&w.head->hint, bits);
+        }
       }
     };
-    if (published) publish_prefix(s_out);
-    const double s_end = chain_emit(v, len, s_in, cdf + off, lane, w.head->diag);
-    if (!published) {
-      publish_prefix(s_end);
+    if (early) hand_on(s_end);
+    if (len > 0) {
+      const double s_walk = chain_emit(v, len, s_start, cdf + off, lane, w.head->diag);
+      if (!early) s_end = s_walk;
+    }
+    if (!early) {
+      hand_on(s_end);
       if (lane == 0) atomicAdd(w.head->diag + 5, 1ull);
     }
+    if (g > 0 && wid == kChainWarps - 1 && lane == 0) atomicAdd(w.head->diag + 9, global_ns() - sm.hint);
   }
 }
 
@@ -1294,7 +1414,7 @@ int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_st
     int igrid = (int)((words + 256 * 8 - 1) / (256 * 8));
     if (igrid > sm_count() * 4) igrid = sm_count() * 4;
     cdf_chain_init_kernel<<<igrid < 1 ? 1 : igrid, 256, 0, st>>>(chain, ntiles, reinterpret_cast<int*>(workspace));
-    int64_t grid = (ntiles + kChainWarps - 1) / kChainWarps;
+    int64_t grid = ntiles;                                  // one CTA per tile in flight, tiles by ticket
     if (grid > (int64_t)per_sm * sm_count()) grid = (int64_t)per_sm * sm_count();
     cdf_chain_kernel<<<(unsigned)grid, 32 * kChainWarps, 0, st>>>(p, n, cdf, chain, ntiles, reinterpret_cast<int*>(workspace));
     TB_CHECK_LAUNCH();

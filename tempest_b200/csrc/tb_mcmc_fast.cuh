@@ -35,6 +35,7 @@ static __constant__ double c_mode[kConstDoubles];
 template <int D, bool TPCN, bool TAPE, bool KONE, int LIKE>
 struct FastBody {
   static constexpr bool kSingleMode = KONE;
+  static constexpr bool kDeferred = true;       // run_steps drives pass() with the deferred-redraw list
   static constexpr int kWarps = 4;
   static constexpr int CM_CHOL = D, CM_INV = D + D * D, CM_PRIOR = D + 2 * D * D, CM_DOF = D + 2 * D * D + 2 * D;
 
@@ -43,8 +44,10 @@ struct FastBody {
   __host__ __device__ static size_t cta_doubles(const tb_mcmc_params& p) {
     return KONE ? 0 : (size_t)p.n_modes * D + 2 * (size_t)p.n_modes * D * D + p.n_modes + 2 * D;
   }
-  // per-warp area: proposal centre / winning proposal [D][32], proposal scale [32], attempts used [32], mode [32]
-  __host__ __device__ static size_t warp_doubles(const tb_mcmc_params&) { return (size_t)D * 32 + 32 + 32; }
+  // per-warp area: proposal centre / winning proposal [D][32], proposal scale [32], attempts used [32], mode [32],
+  // deferred-redraw list (walker, attempts consumed) [kDeferCap] each
+  __host__ __device__ static size_t warp_doubles(const tb_mcmc_params&) { return (size_t)D * 32 + 32 + 32 + kDeferCap; }
+  __device__ static int* defer_list(double* s_warp) { return reinterpret_cast<int*>(s_warp + D * 32 + 32 + 32); }
 
   __device__ static void stage(const StepArgs& a, double* s_body) {
     if (KONE) return;
@@ -65,8 +68,12 @@ struct FastBody {
     for (int e = threadIdx.x; e < 2 * D; e += B) s_prior[e] = __ldg(a.p.prior_params + e);
   }
 
-  __device__ static __forceinline__ void tile(const StepArgs& a, double* s_body, double* s_warp, const double* s_ctrl,
-                                              int64_t tile, int step, TileAcc& acc, double* warp_alpha) {
+  // One pass over up to 32 walkers: lane's walker k (< 0: none) with att0 attempts already consumed.  single_round:
+  // evaluate ONE round of the cooperative redraw only and report the walkers that are still outside the cube in
+  // `deferred` (their consumed attempts in att_out) instead of redrawing them here; they skip phase C.
+  __device__ static __forceinline__ void pass(const StepArgs& a, double* s_body, double* s_warp, const double* s_ctrl,
+                                              const int64_t k, const int att0, const bool single_round, int step,
+                                              TileAcc& acc, double* warp_alpha, unsigned& deferred, int& att_out) {
     const int K = a.p.n_modes;
     const double* s_mean = s_body;
     const double* s_chol = s_mean + K * D;
@@ -102,10 +109,9 @@ struct FastBody {
     };
 
     const int lane = threadIdx.x & 31;
-    const int64_t k = tile * 32 + lane;
-    const bool valid = k < a.n;
+    const bool valid = k >= 0 && k < a.n;
     const Philox rng(a.p.seed, a.p.iteration);
-    const uint64_t slot0 = (uint64_t)(a.p.slot_offset + tile * 32);     // slot of the tile's walker 0
+    const uint64_t slot = (uint64_t)(a.p.slot_offset + (valid ? k : 0));   // global walker slot: the Philox counter
     const bool tape_over = TAPE && step >= a.tape.steps;
     int err = tape_over ? 1 : 0;
     int c = 0;
@@ -132,7 +138,7 @@ struct FastBody {
         } else q = a.qcur[k];
         double g;
         if (TAPE) g = tape_over ? 1.0 : a.tape.gamma[(int64_t)step * a.n + k];
-        else g = gamma_mt(rng, slot0 + lane, (uint32_t)step, 0.5 * ((double)D + dof), acc_word, have_acc_word);
+        else g = gamma_mt(rng, slot, (uint32_t)step, 0.5 * ((double)D + dof), acc_word, have_acc_word);
         const double gscale = 2.0 / (dof + q);
         cm = sig * sqrt(1.0 / (gscale * g));
         keep = sqrt(__dsub_rn(1.0, __dmul_rn(sig, sig)));
@@ -149,7 +155,7 @@ struct FastBody {
     __syncwarp();
     // ---- phase B: warp-cooperative redraw --------------------------------------------------------
     {
-      int att = 0;                                          // next attempt index of MY walker
+      int att = att0;                                       // next attempt index of MY walker
       const int n_att_tape = (TAPE && valid && !tape_over) ? a.tape.z_cnt[(int64_t)step * a.n + k] : 0;
       unsigned pending = __ballot_sync(0xffffffffu, valid && !tape_over);
       while (pending) {
@@ -165,12 +171,12 @@ struct FastBody {
         bool have = true;
         if (TAPE) {
           have = aidx < natt_sel;
-          const int64_t gk = tile * 32 + wsel;
+          const int64_t gk = __shfl_sync(0xffffffffu, k, wsel);
           const double* zt = a.tape.z + a.tape.z_off[(int64_t)step * a.n + gk] + (int64_t)(have ? aidx : 0) * D;
 #pragma unroll
           for (int i = 0; i < D; ++i) z[i] = zt[i];
         } else {
-          normals_fixed<D>(rng, slot0 + (uint64_t)wsel, (uint32_t)step, aidx, z);
+          normals_fixed<D>(rng, __shfl_sync(0xffffffffu, slot, wsel), (uint32_t)step, aidx, z);
         }
         double prop[D];
         bool inside = have;
@@ -209,7 +215,10 @@ struct FastBody {
           }
         }
         pending = __ballot_sync(0xffffffffu, still);
+        if (single_round) break;
       }
+      deferred = pending;            // non-zero only after a single round
+      att_out = att;
     }
     __syncwarp();
     // ---- phase C -------------------------------------------------------------------------------
@@ -243,7 +252,7 @@ struct FastBody {
       alpha = al;
       double ur;
       if (TAPE) ur = a.tape.acc_u[(int64_t)step * a.n + k];
-      else ur = accept_uniform(rng, slot0 + lane, (uint32_t)step, acc_word, have_acc_word);
+      else ur = accept_uniform(rng, slot, (uint32_t)step, acc_word, have_acc_word);
       if (ur < al) {
         acc.accepted += 1;
         double* urow = a.u + k * D;

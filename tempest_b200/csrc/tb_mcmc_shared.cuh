@@ -11,9 +11,10 @@ constexpr int kMcmcBlock = 128;      // walkers per CTA of the per-launch runtim
 constexpr int kRunWarpsMax = 8;      // upper bound on BODY::kWarps (warps per CTA of the persistent kernels)
 constexpr int kMaxModes = 64;
 constexpr int kMaxAttempts = 100000;
+constexpr int kDeferCap = 64;        // deferred-redraw list entries per warp (flushed whenever 32 are waiting)
 
 // control block indices (doubles)
-enum { C_STEPS = 0, C_DONE = 1, C_NACC = 2, C_MEAN_ALPHA = 3, C_ERR = 4, C_NPROP = 5, C_SIGMA0 = 6, C_BASE = 8 };
+enum { C_STEPS = 0, C_DONE = 1, C_NACC = 2, C_MEAN_ALPHA = 3, C_ERR = 4, C_NPROP = 5, C_SIGMA0 = 6, C_ATT_RATIO = 7, C_BASE = 8 };
 __host__ __device__ inline int ctrl_doubles(int K) { return C_BASE + 4 * K + 3; }
 
 struct McmcWs {          // workspace of the per-launch kernel (tb_mcmc_propose / tb_mcmc_accept)
@@ -186,6 +187,7 @@ static __device__ __noinline__ void apply_step_update(const tb_mcmc_params& p, d
   ctrl[C_NACC] = tot[K];
   ctrl[C_MEAN_ALPHA] = all_alpha / n_all;
   ctrl[C_NPROP] += tot[K + 1];
+  ctrl[C_ATT_RATIO] = tot[K + 1] / n_all;          // proposals drawn per walker in this step (1 = no redraws)
   if (tot[K + 2] != 0.0) ctrl[C_ERR] = tot[K + 2];
   if (it >= stop_at || tot[K + 2] != 0.0) ctrl[C_DONE] = 1.0;
 }
@@ -234,6 +236,7 @@ __device__ __forceinline__ void run_steps(const StepArgs& a, double* dyn_smem) {
   const int64_t gw = (int64_t)blockIdx.x * NWARP + wid;
   ColumnFold fold;
   fold.max_cols = 1ull << (K + 2 < 64 ? K + 2 : 63);
+  __shared__ int s_left[kRunWarpsMax];       // deferred walkers each warp has left at the end of a step
   for (int s = 0; s < a.max_steps; ++s) {
     const int step = (int)s_ctrl[C_STEPS];
     TileAcc acc;
@@ -242,8 +245,85 @@ __device__ __forceinline__ void run_steps(const StepArgs& a, double* dyn_smem) {
     if (lane < W) warp_alpha[lane] = 0.0;
     for (int c = 32 + lane; c < W; c += 32) warp_alpha[c] = 0.0;
     __syncwarp();
-    for (int64_t tile = gw; tile < n_tiles; tile += total_warps)
-      BODY::tile(a, s_body, s_warp, s_ctrl, tile, step, acc, warp_alpha);
+    if constexpr (BODY::kDeferred) {
+      // Redraws are pooled over the warp's tiles.  A tile takes ONE round of proposals; walkers that are still outside
+      // the unit cube go to a per-warp list (walker, attempts consumed) and are redrawn 32 at a time -- a full warp of
+      // cooperative attempts -- as soon as 32 are waiting, the rest at the end of the step.  Per-tile redraw loops
+      // otherwise cost a whole extra round whenever ONE of 32 walkers misses (half of all tiles at a 2 % miss rate)
+      // and the spread of those rounds between warps is paid at the grid barrier of every step.  When most proposals
+      // miss (first iterations) the tiles run their redraw loops to completion as before.  Which lane evaluates an
+      // attempt never matters: variates are keyed by (walker slot, step, attempt).
+      const double ratio = s_ctrl[C_ATT_RATIO];
+      const bool defer = !(ratio >= 1.3);
+      int* list_k = BODY::defer_list(s_warp);
+      int* list_att = list_k + kDeferCap;
+      int cnt = 0;
+      int64_t tile = gw;
+      int64_t pooled_k = -2;
+      int pooled_att = 0;
+      bool last = false;
+      for (;;) {                       // ONE call site of the (large, fully unrolled) pass body
+        int64_t k;
+        int att0;
+        bool single;
+        if (cnt >= 32) {                 // a full warp of deferred walkers
+          cnt -= 32;
+          k = (int64_t)list_k[cnt + lane];
+          att0 = list_att[cnt + lane];
+          single = false;
+          __syncwarp();
+        } else if (pooled_k != -2) {     // this warp's share of the CTA's pooled leftovers (set below, once per step)
+          k = pooled_k;
+          att0 = pooled_att;
+          single = false;
+          pooled_k = -2;
+          last = true;
+        } else if (tile < n_tiles) {
+          k = tile * 32 + lane;
+          if (k >= a.n) k = -1;
+          att0 = 0;
+          single = defer;
+          tile += total_warps;
+        } else {
+          if (last) break;
+          // leftovers (< 32 per warp) are pooled over the CTA's warps: at a 0.3 % miss rate every warp would otherwise
+          // spend a whole pass on one or two walkers at the end of every step
+          last = true;
+          if (lane == 0) s_left[wid] = cnt;
+          __syncthreads();
+          int total = 0, mine_w = -1, mine_i = 0;
+          const int want = 32 * wid + lane;                  // warp c takes entries [32 c, 32 c + 32) of the concatenation
+          for (int wv = 0; wv < NWARP; ++wv) {
+            const int c = s_left[wv];
+            if (want >= total && want < total + c) { mine_w = wv; mine_i = want - total; }
+            total += c;
+          }
+          cnt = 0;
+          if (32 * wid >= total) break;
+          if (mine_w >= 0) {
+            const int* lk = BODY::defer_list(s_body + body_cta + (size_t)mine_w * body_warp);
+            pooled_k = lk[mine_i];
+            pooled_att = lk[kDeferCap + mine_i];
+          } else pooled_k = -1;
+          continue;
+        }
+        unsigned def = 0u;
+        int att = 0;
+        BODY::pass(a, s_body, s_warp, s_ctrl, k, att0, single, step, acc, warp_alpha, def, att);
+        if (def) {
+          if ((def >> lane) & 1u) {
+            const int pos = cnt + __popc(def & ((1u << lane) - 1u));
+            list_k[pos] = (int)k;
+            list_att[pos] = att;
+          }
+          cnt += __popc(def);
+          __syncwarp();
+        }
+      }
+    } else {
+      for (int64_t tile = gw; tile < n_tiles; tile += total_warps)
+        BODY::tile(a, s_body, s_warp, s_ctrl, tile, step, acc, warp_alpha);
+    }
     // warp row (fixed lane order), CTA row (fixed warp order)
     {
       const double na = warp_sum((double)acc.accepted), npr = warp_sum((double)acc.nprop), ne = warp_max((double)acc.err);

@@ -19,6 +19,7 @@ struct SmemCol {                     // column `lane` of a [d][32] shared array,
 template <bool TPCN, bool TAPE>
 struct WideBody {
   static constexpr bool kSingleMode = false;
+  static constexpr bool kDeferred = false;
   static constexpr int kWarps = 1;
   __host__ __device__ static size_t cta_doubles(const tb_mcmc_params&) { return 0; }
   // per-warp: proposal centre / winner [d][32], lane-private normals [d][32], lane-private proposal [d][32],

@@ -98,8 +98,12 @@ __device__ __forceinline__ void probe1(Ess3& e, double& chk, double a) {
   if (d > -40.0) { const double w = exp_neg40(d); e.s1 += w; e.s2 = fma(w, w, e.s2); }
 }
 
+// NB probes (betas) share ONE pass over (logl, C): the bytes are read once, every beta keeps its own accumulator
+// and sees the particles in the same order as a single-beta pass, so each triple is bitwise what NB = 1 gives.
+template <int NB>
 __device__ __forceinline__ void probe_slice(const double* __restrict__ logl, const double* __restrict__ C,
-                                            int64_t n, double beta, Ess3& e, double& bad, bool reverse = false) {
+                                            int64_t n, const double (&beta)[NB], Ess3 (&e)[NB], double& bad,
+                                            bool reverse = false) {
   // vectorised 2 x fp64 loads, 4 independent 16-byte loads in flight per thread
   const int64_t n2 = n >> 1;
   const double2* l2 = reinterpret_cast<const double2*>(logl);
@@ -107,17 +111,28 @@ __device__ __forceinline__ void probe_slice(const double* __restrict__ logl, con
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double chk = 0.0;
+  auto four = [&](const double2& la, const double2& ca, const double2& lb, const double2& cb) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      probe4(e[j], chk, __dsub_rn(__dmul_rn(la.x, beta[j]), ca.x), __dsub_rn(__dmul_rn(la.y, beta[j]), ca.y),
+             __dsub_rn(__dmul_rn(lb.x, beta[j]), cb.x), __dsub_rn(__dmul_rn(lb.y, beta[j]), cb.y));
+  };
+  auto two = [&](const double2& la, const double2& ca) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      probe1(e[j], chk, __dsub_rn(__dmul_rn(la.x, beta[j]), ca.x));
+      probe1(e[j], chk, __dsub_rn(__dmul_rn(la.y, beta[j]), ca.y));
+    }
+  };
   if (!reverse) {
     for (; i + stride < n2; i += 2 * stride) {
       const double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
       const double2 lb = __ldg(l2 + i + stride), cb = __ldg(c2 + i + stride);
-      probe4(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x), __dsub_rn(__dmul_rn(la.y, beta), ca.y),
-             __dsub_rn(__dmul_rn(lb.x, beta), cb.x), __dsub_rn(__dmul_rn(lb.y, beta), cb.y));
+      four(la, ca, lb, cb);
     }
     for (; i < n2; i += stride) {
       const double2 la = __ldg(l2 + i), ca = __ldg(c2 + i);
-      probe1(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x));
-      probe1(e, chk, __dsub_rn(__dmul_rn(la.y, beta), ca.y));
+      two(la, ca);
     }
   } else if (i < n2) {
     // same elements, last to first: the tail of the previous (forward) pass is still in L2
@@ -126,18 +141,26 @@ __device__ __forceinline__ void probe_slice(const double* __restrict__ logl, con
     for (; cnt >= 2; cnt -= 2, j -= 2 * stride) {
       const double2 la = __ldg(l2 + j), ca = __ldg(c2 + j);
       const double2 lb = __ldg(l2 + j - stride), cb = __ldg(c2 + j - stride);
-      probe4(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x), __dsub_rn(__dmul_rn(la.y, beta), ca.y),
-             __dsub_rn(__dmul_rn(lb.x, beta), cb.x), __dsub_rn(__dmul_rn(lb.y, beta), cb.y));
+      four(la, ca, lb, cb);
     }
     if (cnt == 1) {
       const double2 la = __ldg(l2 + j), ca = __ldg(c2 + j);
-      probe1(e, chk, __dsub_rn(__dmul_rn(la.x, beta), ca.x));
-      probe1(e, chk, __dsub_rn(__dmul_rn(la.y, beta), ca.y));
+      two(la, ca);
     }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
-    probe1(e, chk, __dsub_rn(__dmul_rn(logl[n - 1], beta), C[n - 1]));
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) probe1(e[j], chk, __dsub_rn(__dmul_rn(logl[n - 1], beta[j]), C[n - 1]));
+  }
   if (chk != chk) bad += 1.0;      // some a_s was NaN or +-inf (reported as a non-zero count)
+}
+__device__ __forceinline__ void probe_slice(const double* __restrict__ logl, const double* __restrict__ C,
+                                            int64_t n, double beta, Ess3& e, double& bad, bool reverse = false) {
+  const double b1[1] = {beta};
+  Ess3 e1[1];
+  e1[0] = e;
+  probe_slice<1>(logl, C, n, b1, e1, bad, reverse);
+  e = e1[0];
 }
 
 __device__ __forceinline__ void write_probe_result(double* out, const Ess3& e, double bad) {
@@ -149,34 +172,38 @@ __device__ __forceinline__ void write_probe_result(double* out, const Ess3& e, d
 
 // Row fold of grid_xreduce for (m, S1, S2, n_nonfinite) rows: Ess3 merges in a fixed order.
 struct EssFold {
-  // all threads of the CTA; thread t merges rows t, t + B, ... in ascending order, then the fixed-order CTA merge
-  __device__ void rows(const double* rows, int nb, int W, double* tot) const {
+  // rows are [nb][4] = nb x (m, S1, S2, n_nonfinite).  All threads of the CTA; thread t merges rows t, t + B, ... in
+  // ascending order, then the fixed-order CTA merge -- per triple exactly what the single-triple fold does.
+  int nb = 1;
+  __device__ void rows(const double* rows, int nrows, int W, double* tot) const {
     __shared__ double s_m[3 * 32 + 8];
     __shared__ double s_b[40];
-    Ess3 e; e.init();
-    double bad = 0.0;
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-      const double* r = rows + (size_t)b * W;
-      e.merge(__ldcg(r), __ldcg(r + 1), __ldcg(r + 2));
-      bad += __ldcg(r + 3);
+    for (int j = 0; j < nb; ++j) {
+      Ess3 e; e.init();
+      double bad = 0.0;
+      for (int b = threadIdx.x; b < nrows; b += blockDim.x) {
+        const double* r = rows + (size_t)b * W + 4 * j;
+        e.merge(__ldcg(r), __ldcg(r + 1), __ldcg(r + 2));
+        bad += __ldcg(r + 3);
+      }
+      block_merge_ess3(e, s_m);
+      bad = block_sum(bad, s_b);
+      if (threadIdx.x == 0) { tot[4 * j] = e.m; tot[4 * j + 1] = e.s1; tot[4 * j + 2] = e.s2; tot[4 * j + 3] = bad; }
+      __syncthreads();
     }
-    block_merge_ess3(e, s_m);
-    bad = block_sum(bad, s_b);
-    if (threadIdx.x == 0) { tot[0] = e.m; tot[1] = e.s1; tot[2] = e.s2; tot[3] = bad; }
-    __syncthreads();
   }
   __device__ void ranks(const double* slots, int world, int W, double* tot) const {
     const int lane = threadIdx.x & 31;
-    if (lane == 0) {
+    if (lane < nb) {
       Ess3 g; g.init();
       double gb = 0.0;
       for (int r = 0; r < world; ++r) {
         const double* slot = slots + (size_t)r * kXSlotDoubles;
         (void)ld_acquire_sys(reinterpret_cast<const unsigned long long*>(slot));
-        g.merge(ld_relaxed_sys(slot + 1), ld_relaxed_sys(slot + 2), ld_relaxed_sys(slot + 3));
-        gb += ld_relaxed_sys(slot + 4);
+        g.merge(ld_relaxed_sys(slot + 1 + 4 * lane), ld_relaxed_sys(slot + 2 + 4 * lane), ld_relaxed_sys(slot + 3 + 4 * lane));
+        gb += ld_relaxed_sys(slot + 4 + 4 * lane);
       }
-      tot[0] = g.m; tot[1] = g.s1; tot[2] = g.s2; tot[3] = gb;
+      tot[4 * lane] = g.m; tot[4 * lane + 1] = g.s1; tot[4 * lane + 2] = g.s2; tot[4 * lane + 3] = gb;
     }
   }
 };
@@ -218,79 +245,152 @@ constexpr double kBetaTol = 1e-4, kBetaRtol = 1e-8, kEssTol = 0.01, kMetricAtol 
 constexpr int kMaxBisect = 200;                                                          // reweight.py:121
 constexpr double kTiny = 2.2250738585072014e-308;
 
-__global__ void __launch_bounds__(kBlock, 5)
+// State of the reference's search (reweight.py:255-297 bracket, :165-211 bisection), advanced one probe at a time.
+struct BetaSearch {
+  int phase;                 // 0: probe beta_prev, 1: probe 1.0, 2: bracket, 3: bisect
+  double lo, hi, bmin, bmax;
+  int nbis, same;
+};
+// Consume ESS(beta).  Returns true when the search ends at `beta`; otherwise `next` is the beta to probe next.
+__device__ __forceinline__ bool search_advance(BetaSearch& s, double beta, double ess, double target, double beta_prev,
+                                               double& next) {
+  bool done = false;
+  next = beta;
+  if (s.phase == 0) {                       // reweight.py:264-266
+    if (ess <= target) { done = true; s.same = 1; }
+    else { s.phase = 1; next = 1.0; }
+  } else if (s.phase == 1) {                // :269-271
+    if (ess >= target) { done = true; s.same = 1; }
+    else s.phase = 2;
+  } else if (s.phase == 2) {                // :288-295
+    if (ess >= target) s.lo = beta; else s.hi = beta;
+  } else {                                  // :165-211
+    const double val = isfinite(ess) ? ess : 1e10;
+    const bool metric_ok = fabs(val - target) < fmax(kEssTol * fabs(target), kMetricAtol);
+    const double scale = fmax(fmax(fabs(s.bmin), fabs(s.bmax)), kTiny);
+    const bool beta_ok = (s.bmax - s.bmin) < fmax(kBetaRtol * scale, kBetaTol * scale);
+    ++s.nbis;
+    if (metric_ok || beta_ok || beta == 1.0 || s.nbis >= kMaxBisect) done = true;
+    else if (val < target) s.bmax = beta; else s.bmin = beta;
+  }
+  if (!done && s.phase == 2) {              // :277-287
+    const double mid = (s.hi + s.lo) * 0.5;
+    const double scale = fmax(fmax(fabs(s.lo), fabs(s.hi)), kTiny);
+    if (s.hi - s.lo <= fmax(kBetaRtol * scale, kBetaTol * scale)) {
+      s.phase = 3; s.bmin = beta_prev; s.bmax = s.hi;   // bisect on [beta_prev, beta_high] (:409-414)
+    } else next = mid;
+  }
+  if (!done && s.phase == 3) next = (s.bmax + s.bmin) * 0.5;
+  return done;
+}
+
+// The whole search in one cooperative launch.  A probe is a full pass over the ensemble, and a bisection needs ~25 of
+// them -- but the beta of the NEXT probe is one of two values that are known before the current probe's ESS is (the
+// state machine above, fed "above target" / "below target").  So every pass evaluates three betas on the same bytes:
+// the current one and both possible successors; its result consumes TWO steps of the reference's search.  The probe
+// sequence, the comparisons and the final beta are the reference's, bit for bit; the ensemble is streamed half as often
+// (the e^-40 cut keeps the extra exps off most particles) and the grid-wide / cross-GPU folds happen half as often.
+__global__ void __launch_bounds__(kBlock, 4)
 next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n,
                  double beta_prev, double target, int flags, GridSync* gs, double* __restrict__ result,
                  double* __restrict__ plog, int plog_cap, tb_xgpu xg) {
   __shared__ double smem[160];
-  __shared__ double s_part[4], s_tot[4];
-  __shared__ double sh_beta;
-  __shared__ int sh_done;
+  __shared__ double s_part[12], s_tot[12];
+  __shared__ double sh_beta[3];
+  __shared__ int sh_done, sh_nb;
   // search state, replicated bit-identically in thread 0 of every CTA
-  int phase = (flags & 1) ? 1 : 0;   // 0: probe beta_prev, 1: probe 1.0, 2: bracket, 3: bisect
-  double lo = beta_prev, hi = 1.0, bmin = beta_prev, bmax = 1.0;
-  int nprobe = 0, nbis = 0, same = 0;
-  double beta = (phase == 0) ? beta_prev : 1.0;
+  BetaSearch st;
+  st.phase = (flags & 1) ? 1 : 0;
+  st.lo = beta_prev; st.hi = 1.0; st.bmin = beta_prev; st.bmax = 1.0; st.nbis = 0; st.same = 0;
+  int nprobe = 0, npass = 0;
+  // candidates of the first pass
+  auto plan = [&](const BetaSearch& cur, double beta, double (&b)[3]) -> int {
+    // b[0] = beta; b[1] / b[2] = the next beta if ESS(beta) turns out high / low (absent: the search would end)
+    b[0] = beta; b[1] = beta; b[2] = beta;
+    BetaSearch hi_s = cur, lo_s = cur;
+    double nh = beta, nl = beta;
+    const bool dh = search_advance(hi_s, beta, 1e300, target, beta_prev, nh);
+    const bool dl = search_advance(lo_s, beta, 0.0, target, beta_prev, nl);
+    if (dh && dl) return 1;
+    b[1] = dh ? nl : nh;
+    b[2] = dl ? nh : nl;
+    return 3;
+  };
+  if (threadIdx.x == 0) {
+    double b[3];
+    sh_nb = plan(st, (st.phase == 0) ? beta_prev : 1.0, b);
+    sh_beta[0] = b[0]; sh_beta[1] = b[1]; sh_beta[2] = b[2];
+  }
+  __syncthreads();
   for (;;) {
-    Ess3 e; e.init();
+    const int nb = sh_nb;
+    double beta[3] = {sh_beta[0], sh_beta[1], sh_beta[2]};
+    Ess3 e[3];
+    e[0].init(); e[1].init(); e[2].init();
     double bad = 0.0;
-    probe_slice(logl, C, n, beta, e, bad, (nprobe & 1) != 0);   // alternate direction: reuse what the last pass left in L2
-    block_merge_ess3(e, smem);
-    bad = block_sum(bad, smem + 100);
-    if (threadIdx.x == 0) { s_part[0] = e.m; s_part[1] = e.s1; s_part[2] = e.s2; s_part[3] = bad; }
-    __syncthreads();
-    // one synchronisation point per probe: grid-wide fold, and on >1 GPU the merge of the ranks' triples over
-    // NVLink peer memory, fused (tb_xgpu.cuh); every CTA of every rank ends with the same (m, S1, S2)
-    const int rc = grid_xreduce(gs, xg, nprobe, 4, s_part, s_tot, EssFold());
-    if (threadIdx.x == 0) {
-      e.m = s_tot[0]; e.s1 = s_tot[1]; e.s2 = s_tot[2]; bad = s_tot[3];
-      if (rc) bad = NAN;               // a peer did not answer: stop the search, the host raises
+    const bool reverse = (npass & 1) != 0;      // alternate direction: reuse what the last pass left in L2
+    if (nb == 1) {
+      const double b1[1] = {beta[0]};
+      Ess3 e1[1];
+      e1[0].init();
+      probe_slice<1>(logl, C, n, b1, e1, bad, reverse);
+      e[0] = e1[0];
+    } else {
+      probe_slice<3>(logl, C, n, beta, e, bad, reverse);
     }
+    bad = block_sum(bad, smem + 100);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {              // (static indices keep the accumulators in registers; nb is CTA-uniform)
+      if (j < nb) {
+        block_merge_ess3(e[j], smem);
+        if (threadIdx.x == 0) { s_part[4 * j] = e[j].m; s_part[4 * j + 1] = e[j].s1; s_part[4 * j + 2] = e[j].s2; s_part[4 * j + 3] = bad; }
+        __syncthreads();
+      }
+    }
+    // one synchronisation point per pass: grid-wide fold, and on >1 GPU the merge of the ranks' triples over
+    // NVLink peer memory, fused (tb_xgpu.cuh); every CTA of every rank ends with the same (m, S1, S2) per beta
+    EssFold fold;
+    fold.nb = nb;
+    const int rc = grid_xreduce(gs, xg, npass, 4 * nb, s_part, s_tot, fold);
+    ++npass;
     if (threadIdx.x == 0) {
-      double ess = (e.s1 * e.s1) / e.s2;
-      if (blockIdx.x == 0 && plog != nullptr && nprobe < plog_cap) { plog[2 * nprobe] = beta; plog[2 * nprobe + 1] = ess; }
-      ++nprobe;
       int done = 0;
-      double next = beta;
-      if (phase == 0) {                       // reweight.py:264-266
-        if (ess <= target) { done = 1; same = 1; }
-        else { phase = 1; next = 1.0; }
-      } else if (phase == 1) {                // :269-271
-        if (ess >= target) { done = 1; same = 1; }
-        else phase = 2;
-      } else if (phase == 2) {                // :288-295
-        if (ess >= target) lo = beta; else hi = beta;
-      } else {                                // :165-211
-        double val = isfinite(ess) ? ess : 1e10;
-        bool metric_ok = fabs(val - target) < fmax(kEssTol * fabs(target), kMetricAtol);
-        double scale = fmax(fmax(fabs(bmin), fabs(bmax)), kTiny);
-        bool beta_ok = (bmax - bmin) < fmax(kBetaRtol * scale, kBetaTol * scale);
-        ++nbis;
-        if (metric_ok || beta_ok || beta == 1.0 || nbis >= kMaxBisect) done = 1;
-        else if (val < target) bmax = beta; else bmin = beta;
+      double cur = beta[0], next = beta[0];
+      int j = 0;                               // which evaluated beta is being consumed
+      for (int level = 0; level < 2 && !done; ++level) {
+        Ess3 r;
+        r.m = s_tot[4 * j]; r.s1 = s_tot[4 * j + 1]; r.s2 = s_tot[4 * j + 2];
+        double rb = s_tot[4 * j + 3];
+        if (rc) rb = NAN;                      // a peer did not answer: stop the search, the host raises
+        const double ess = (r.s1 * r.s1) / r.s2;
+        if (blockIdx.x == 0 && plog != nullptr && nprobe < plog_cap) { plog[2 * nprobe] = cur; plog[2 * nprobe + 1] = ess; }
+        ++nprobe;
+        done = search_advance(st, cur, ess, target, beta_prev, next) ? 1 : 0;
+        if (rb != rb) done = 1;
+        if (done) {
+          if (blockIdx.x == 0) {
+            result[0] = cur; result[1] = r.m; result[2] = r.s1; result[3] = r.s2; result[4] = ess;
+            result[5] = r.m + log(r.s1); result[6] = (double)nprobe; result[7] = (double)st.same;
+            result[8] = rb; result[9] = (double)npass;
+          }
+          break;
+        }
+        if (level == 0) {
+          if (nb == 3 && next == beta[1]) j = 1;
+          else if (nb == 3 && next == beta[2]) j = 2;
+          else break;                          // successor was not evaluated in this pass (cannot happen with nb == 3)
+          cur = next;
+        }
       }
-      if (!done && phase == 2) {              // :277-287
-        double mid = (hi + lo) * 0.5;
-        double scale = fmax(fmax(fabs(lo), fabs(hi)), kTiny);
-        if (hi - lo <= fmax(kBetaRtol * scale, kBetaTol * scale)) {
-          phase = 3; bmin = beta_prev; bmax = hi;   // bisect on [beta_prev, beta_high] (:409-414)
-        } else next = mid;
+      if (!done) {
+        double b[3];
+        sh_nb = plan(st, next, b);
+        sh_beta[0] = b[0]; sh_beta[1] = b[1]; sh_beta[2] = b[2];
       }
-      if (!done && phase == 3) next = (bmax + bmin) * 0.5;
-      if (bad != bad) done = 1;
-      if (done && blockIdx.x == 0) {
-        result[0] = beta; result[1] = e.m; result[2] = e.s1; result[3] = e.s2; result[4] = ess;
-        result[5] = e.m + log(e.s1); result[6] = (double)nprobe; result[7] = (double)same;
-        result[8] = bad;
-      }
-      sh_beta = next;
       sh_done = done;
     }
     __syncthreads();
     if (sh_done) break;
-    beta = sh_beta;
-    // thread 0 keeps the authoritative state; other threads only need beta / nprobe parity
-    if (threadIdx.x != 0) ++nprobe;
   }
 }
 
@@ -322,7 +422,7 @@ int tb_mixture_append(const double* logl, double* C, int64_t n_old, int64_t n_ne
 }
 
 // one allocation serves both kernels: [ProbeWs of probe_kernel | GridSync + rows of next_beta_kernel]
-size_t tb_probe_workspace_bytes(void) { return sizeof(ProbeWs) + grid_sync_bytes(kMaxPartials, 4); }
+size_t tb_probe_workspace_bytes(void) { return sizeof(ProbeWs) + grid_sync_bytes(kMaxPartials, 12); }
 size_t tb_next_beta_workspace_bytes(void) { return tb_probe_workspace_bytes(); }
 
 int tb_probe(const double* logl, const double* C, int64_t n, double beta, void* workspace, double* out6,
@@ -374,7 +474,7 @@ int tb_next_beta_x(const double* logl, const double* C, int64_t n, double beta_p
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, next_beta_kernel, kBlock, 0);
     if (e != cudaSuccess) return (int)e;
-    if (per_sm > 5) per_sm = 5;
+    if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) return TB_ERR_UNSUPPORTED;
     max_coresident = per_sm * tb::sm_count();
     if (max_coresident > kMaxPartials) max_coresident = kMaxPartials;

@@ -145,6 +145,7 @@ __device__ __noinline__ int grid_xreduce(GridSync* gs, const tb_xgpu& x, int k, 
       const unsigned long long t0 = global_ns();
       while (ld_acquire_gpu(&gs->bflag[par]) != seq) {
         if (global_ns() - t0 > 2 * kXSpinBudgetNs) { s_bad = 1; break; }
+        __nanosleep(40);      // the pollers of finished CTAs took ~15 % of the issue slots from the warps still working
       }
     }
   }
@@ -163,6 +164,57 @@ struct ColumnFold {
   __device__ void rows(const double* rows, int nb, int W, double* tot) const {
     __shared__ double s_w[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5, B = blockDim.x;
+    if (W <= 4 && nw <= 8) {
+      // narrow rows (single-mode runs: sum alpha, accepted, proposals, error): every thread folds whole rows, so the
+      // columns share one pass over the rows, one warp reduction each and ONE barrier (the per-column form below
+      // costs two barriers per column on the critical path of every Metropolis step)
+      __shared__ double s_wc[8][4];
+      double v[4][2];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool mx = (max_cols >> c) & 1ull;
+        v[c][0] = v[c][1] = mx ? -INFINITY : 0.0;
+      }
+      int b = threadIdx.x;
+      for (; b + B < nb; b += 2 * B) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < W) {
+            const bool mx = (max_cols >> c) & 1ull;
+            const double r0 = __ldcg(rows + (size_t)b * W + c), r1 = __ldcg(rows + (size_t)(b + B) * W + c);
+            v[c][0] = mx ? fmax(v[c][0], r0) : v[c][0] + r0;
+            v[c][1] = mx ? fmax(v[c][1], r1) : v[c][1] + r1;
+          }
+        }
+      }
+      if (b < nb) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < W) {
+            const bool mx = (max_cols >> c) & 1ull;
+            const double r0 = __ldcg(rows + (size_t)b * W + c);
+            v[c][0] = mx ? fmax(v[c][0], r0) : v[c][0] + r0;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool mx = (max_cols >> c) & 1ull;
+        double x = mx ? fmax(v[c][0], v[c][1]) : v[c][0] + v[c][1];
+        x = mx ? warp_max(x) : warp_sum(x);
+        if (lane == 0) s_wc[wid][c] = x;
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < W) {
+        const int c = threadIdx.x;
+        const bool mx = (max_cols >> c) & 1ull;
+        double t = s_wc[0][c];
+        for (int i = 1; i < nw; ++i) t = mx ? fmax(t, s_wc[i][c]) : t + s_wc[i][c];
+        tot[c] = t;
+      }
+      __syncthreads();
+      return;
+    }
     for (int c = 0; c < W; ++c) {
       const bool mx = c < 64 && ((max_cols >> c) & 1ull);
       const double id = mx ? -INFINITY : 0.0;

@@ -645,13 +645,14 @@ class Reweighter:
         if timing is not None:
             ev1.record()
         h = res.cpu().numpy()
-        nprobe = int(h[6])
-        if timing is not None:           # (events, particle-probes of this launch)
-            timing.setdefault("next_beta", []).append((ev0, ev1, float(nprobe) * ens.n_total))
+        nprobe, npass = int(h[6]), int(h[9])     # probes consumed by the search / passes over the ensemble (3 betas each)
+        if timing is not None:           # (events, particle-passes of this launch, particle-probes)
+            timing.setdefault("next_beta", []).append((ev0, ev1, float(npass) * ens.n_total))
+            timing.setdefault("next_beta_probes", []).append((ev0, ev1, float(nprobe) * ens.n_total))
         hp = plog[: 2 * min(nprobe, 512)].cpu().numpy().reshape(-1, 2)
         self.probe_log.extend((float(b), float(e)) for b, e in hp)
         if k.sharded:
-            k.consume_exchanges(nprobe)              # one peer-memory exchange per probe
+            k.consume_exchanges(npass)               # one peer-memory exchange per pass
         if h[8] != 0.0:
             raise FloatingPointError(f"{int(h[8])} non-finite log-weights in the persistent ensemble")
         self._logz_host = float(h[5])                  # logZ(beta) of the last probe is already on the host

@@ -36,10 +36,14 @@ for chain in (1, 0):
             f"{16.0 * ens.n_total / ms / 1e6:.0f} GB/s by 16 B/element ({16.0 * ens.n_total / ms / 1e6 / peak:.3f} of {peak} GB/s); "
             f"status {ws[:64].view(torch.int32).cpu().numpy()[:14].tolist()}")
     if chain:
+        nt = max(1, int(ws[:4].view(torch.int32)[0].item()))
         off = int(k.lib.tb_cdf_chain_diag_ptr(ptr(ws), ens.n_total)) - ws.data_ptr()
-        dg = ws[off: off + 48].view(torch.int64).cpu().numpy().tolist()
+        dg = ws[off: off + 192].view(torch.int64).cpu().numpy().tolist()
         line += (f"; chain diag: multi-round tiles {dg[0]}, rounds in them {dg[1]}, look-back retries {dg[2]}, "
-                 f"re-publications {dg[3]}, serial elements {dg[4]}, late prefixes {dg[5]}")
+                 f"re-publications {dg[3]}, serial elements {dg[4]}, late prefixes {dg[5]}, look-back rounds {dg[6]}; "
+                 f"us per tile: load+aggregate {dg[7] / 1e3 / nt:.2f}, look-back {dg[8] / 1e3 / nt:.2f}, emit {dg[9] / 1e3 / nt:.2f}; "
+                 f"failed attempts by reason: not-ready {dg[10]}, tile0 {dg[11]}, all-invalid {dg[12]}, no-offer {dg[13]}, "
+                 f"exhausted {dg[14]}, prefix-not-regime {dg[15]}, binade-mismatch {dg[16]}, overflow {dg[17]}")
     print(line)
     print("   bitwise equal to numpy:", np.array_equal(ref.view(np.uint64), cdf.cpu().numpy().view(np.uint64)))
 k.lib.tb_cdf_set_chain(1)
