@@ -391,6 +391,8 @@ def main():
     stage_ms = dict(stage_acc)
 
     # ---- end to end through the public API (host in, host out) -----------------------------------------
+    del core, s                                # (sharded runs: hands the pooled peer-memory buffers back, as a user's
+    gc.collect()                               #  previous Sampler going out of scope would)
     barrier()
     t0 = time.perf_counter()
     s2 = new_sampler()

@@ -76,6 +76,9 @@ int tb_log_weights(const double* logl, const double* C, int64_t n_total, double 
  * logic and constants (steps/reweight.py:123-297, config.py:233-237) in ONE cooperative
  * launch -- no host round trip per probe.
  *   flags bit0: skip the "ESS(beta_prev) <= target -> stay" probe (host already decided it).
+ *   flags bit1: speculative passes -- every pass evaluates the current beta and both possible successors (same probe
+ *   sequence and result, half the passes; fp64-bound, measured slower on one B200: off by default).
+ *   result16[9] = passes over the ensemble (= exchanges on > 1 GPU); result16[6] = probes consumed by the search.
  *   result16[0]=beta, [1]=m, [2]=S1, [3]=S2, [4]=ESS, [5]=logZ(beta), [6]=n_probes,
  *   [7]=beta_low==beta_high flag, [8]=non-finite count; probe_log (may be NULL) receives
  *   (beta,ESS) pairs, at most probe_log_cap pairs.  logl and C must be 16-byte aligned. */
@@ -93,12 +96,14 @@ int tb_next_beta(const double* logl, const double* C, int64_t n_total, double be
  * ---------------------------------------------------------------------------------- */
 size_t tb_cdf_workspace_bytes(int64_t n);
 int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_stream_t stream);
-/* tb_cdf_exact runs ONE streaming kernel on a single GPU (chained scan with decoupled look-back that carries the exact
- * running sum; reads p once, writes cdf once).  tb_cdf_set_chain(0) selects the multi-kernel pipeline of
- * tb_cdf_exact_x instead (A/B; also the environment variable TB_CDF_CHAIN=0).  tb_cdf_chain_diag_ptr: device
- * uint64[24] of the last chained call on `workspace` {tiles needing > 1 round, rounds in them, look-back retries,
- * re-published aggregates, serial-regime elements, late prefix publications, look-back rounds, ns summed over tiles
- * ticket -> aggregate, aggregate -> start value, start value -> done, ...}. */
+/* Two single-GPU implementations of tb_cdf_exact, both bit for bit numpy's cumsum: the multi-kernel pipeline of
+ * tb_cdf_exact_x (default) and a chained scan with decoupled look-back that carries the exact running sum (a binade-guess
+ * pass + ONE streaming kernel; tb_cdf_set_chain(1) or the environment variable TB_CDF_CHAIN=1).  On the weight vector
+ * of a C4 run (3.8e7 weights, ~55 multi-binade jumps of the running sum) the chain is the slower one: every jump stalls
+ * all tiles in flight (profiles/r02_cdf_paths.txt).  tb_cdf_chain_diag_ptr: device uint64[24] of the last chained call on
+ * `workspace` {tiles needing > 1 round, rounds in them, look-back retries, re-published aggregates, serial-regime
+ * elements, late prefix publications, look-back rounds, ns summed over tiles ticket -> aggregate, aggregate -> start
+ * value, start value -> done, failed look-back attempts by reason [10..17]}. */
 void tb_cdf_set_chain(int32_t on);
 uint64_t* tb_cdf_chain_diag_ptr(void* workspace, int64_t n);
 /* The same over a SHARDED weight vector.  The global order is generation-major, rank-minor (the order of the
@@ -343,6 +348,8 @@ int tb_search_right_sharded_guided(const double* cdf, int64_t n, const int64_t* 
                                    int64_t m, void* guide, int32_t bits, int64_t* idx, tb_stream_t stream);
 /* w /= denom */
 int tb_scale_inplace(double* w, int64_t n, double denom, tb_stream_t stream);
+/* the same with the divisor read from device memory (sharded runs: the all-reduced sum never visits the host) */
+int tb_scale_inplace_dev(double* w, int64_t n, const double* denom, tb_stream_t stream);
 /* one stage of tb_select_ranks: 0 init, 1 local histogram of `level`, 2 pick from the (all-reduced)
  * histogram, 3 write results; the histogram lives at workspace + tb_select_hist_offset() */
 int tb_select_stage(const double* base, const int64_t* rows, int64_t stride, int64_t n, int32_t ncols,
@@ -490,6 +497,11 @@ int tb_xrows_scatter(const double* hu, const double* hl, int32_t d, const int64_
 /* measurement aid (bench.py): one launch of 8 * n_SM CTAs x 256 threads, each running eight independent
  * register-resident fp64 FMA chains for `iters` iterations = tb_fp64_peak_flops(iters) flop; timed by the
  * caller with CUDA events it gives the fp64 FMA peak the mutation kernel's roofline is quoted against */
+/* Benchmark of the in-kernel synchronisation point of the persistent kernels (tb_xgpu.cuh grid_xreduce): `count`
+ * back-to-back grid-wide (+ cross-GPU when xgpu->world > 1) reductions of a 4-double row in ONE cooperative launch of
+ * `grid` CTAs; out2 = {ns per synchronisation point, checksum}.  Consumes `count` exchange sequence numbers. */
+size_t tb_xgpu_bench_workspace_bytes(int32_t grid);
+int tb_xgpu_bench(const tb_xgpu* xgpu, int32_t grid, int32_t count, void* workspace, double* out2, tb_stream_t stream);
 int64_t tb_fp64_peak_flops(int32_t iters);
 int tb_fp64_peak_run(int32_t iters, double* out, tb_stream_t stream);
 

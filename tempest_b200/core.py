@@ -90,10 +90,28 @@ class SamplerCore:
                 normalize=config.normalize)
         # independent branches of one iteration run on a side stream (single GPU, ESS mode, one mode,
         # multinomial resampling): the cv diagnostic and the resampling overlap with the Trainer
-        self.overlap = (not self.comm.on and config.volume_variation is None and not config.clustering
-                        and config.resample == "mult")
+        self.overlap = (config.volume_variation is None and not config.clustering and config.resample == "mult"
+                        and (not self.comm.on or self.k.comm.fast is not None))
+        import os
+
+        if os.environ.get("TEMPEST_B200_OVERLAP", "1") == "0":
+            self.overlap = False
         self.side = torch.cuda.Stream(self.device) if self.overlap else None
-        self.k_side = Kernels(self.device) if self.overlap else None
+        if self.overlap and self.comm.on:
+            # sharded: the side branches issue collectives of their own, so they get their own peer-memory channel
+            # (a second Comm / PeerCollectives / table memory); both streams issue the same call sequence on every rank
+            from .dist import Comm as _Comm
+
+            self.k_side = ShardedKernels(self.device, _Comm())
+            self.k_side.defer_checks = True
+        else:
+            self.k_side = Kernels(self.device) if self.overlap else None
+        if self.comm.on:
+            from .ensemble import PersistentEnsemble as _PE
+
+            for kk in (self.k, self.k_side):
+                if kk is not None:
+                    kk.prepare(self.n_local, config.n_dim, self.n_global * _PE.RESERVE_GENERATIONS)
         self._cv_pending = None
         self.reweighter = Reweighter(self)
         self.trainer = Trainer(self)
@@ -168,11 +186,14 @@ class SamplerCore:
         ready.record()
         self.side.wait_event(ready)
         with torch.cuda.stream(self.side):
-            ks.volume_variation_begin(ens.u, w_cv, n, d)
+            if self.comm.on:
+                ks.volume_variation_async(ens.u, w_cv, n, d)        # moments + all-reduces + Cholesky, all on the device
+            else:
+                ks.volume_variation_begin(ens.u, w_cv, n, d)
         self._cv_pending = (w_cv, n)
 
     def mid_cv(self) -> None:
-        if self._cv_pending is not None:
+        if self._cv_pending is not None and not self.comm.on:
             w_cv, n = self._cv_pending
             with torch.cuda.stream(self.side):
                 self.k_side.volume_variation_mid(self.ensemble.u, w_cv, n, self.ensemble.n_dim)
@@ -184,7 +205,7 @@ class SamplerCore:
         if self._cv_pending is not None:
             self._cv_pending = None
             with torch.cuda.stream(self.side):
-                cv = self.k_side.volume_variation_end()
+                cv = self.k_side.volume_variation_result() if self.comm.on else self.k_side.volume_variation_end()
             self.state.set_current("cv", cv)
 
     def transform_to_x(self, u: torch.Tensor) -> torch.Tensor:
@@ -277,10 +298,16 @@ class SamplerCore:
         self._stage("resample")
         self.resampler.run(weights)
         self._stage("mutate")
+        if self.comm.on and self.overlap:
+            # the persistent kernels of the mutation / the next ESS search occupy every SM and wait for the peers inside
+            # the kernel: all side-stream collectives must have completed on this GPU before they start
+            torch.cuda.current_stream().wait_stream(self.side)
         self.mutator.run(mode_stats)
         self.end_cv()
         if self.comm.on:
             self.k.check_pending()          # status words of this iteration's sharded cdf calls / peer collectives
+            if self.k_side is not None and hasattr(self.k_side, "check_pending"):
+                self.k_side.check_pending()
         self._stage("commit")
         # commit (state_manager.py:356-416): particles to the device ensemble, scalars to host lists
         st = self.state

@@ -827,15 +827,15 @@ cdf_search_x_kernel(CdfArgs a, const double* __restrict__ draws, int64_t m, doub
 
 
 // =================================================================================================================
-// Single-GPU path: ONE streaming kernel (read p once, write cdf once) -- a chained scan with decoupled look-back in
-// which the carried quantity is the EXACT running sum.
+// Single-GPU path: a guess pass (read p) and ONE streaming kernel (read p, write cdf) -- a chained scan with decoupled
+// look-back in which the carried quantity is the EXACT running sum.
 //
 // A warp owns a 1024-element tile (tiles are handed out by a ticket counter, so a warp only ever waits for tiles that
 // are already running).  Per tile:
 //   1. load the tile into registers; publish its AGGREGATE: the int64 totals of inc() under two candidate binades
-//      (E, E + 1), where E is the binade of the largest exact prefix published so far (a global hint word; the running
-//      sum is monotone, so the hint is a lower bound that is almost always still the right binade).  Each 64-bit
-//      descriptor word is self-describing (binade | total), so readers never see a torn aggregate;
+//      (E, E + 1), where E is a guess of the binade the tile starts in (cdf_guess_* kernels: a 1e-7-accurate prefix of
+//      1024-element sums -- one extra read of p; a tile whose guess has no safe value publishes "no aggregate").  Each
+//      64-bit descriptor word is self-describing (binade | total), so readers never see a torn aggregate;
 //   2. look back over the predecessors' descriptors (32 per round, one per lane) to the nearest tile that has published
 //      its exact inclusive PREFIX s; the tiles in between must all offer a total under the binade of s and the integer
 //      sum must stay below 2^53 -- then s_in = (S + sum of totals) q is exactly numpy's running sum at the tile start.
@@ -861,6 +861,8 @@ struct ChainHead {               // 256 bytes, zeroed by cdf_chain_init_kernel
                                  // 7 / 8 / 9 ns summed over tiles: ticket -> aggregate, aggregate -> start value, start -> done
 };
 __host__ __device__ inline size_t chain_bytes(int64_t ntiles) { return 256 + 3 * align_up(8 * (size_t)(ntiles + 1), 256); }
+// after the descriptors: sub-tile sums (double) and binade guesses (int), kChainWarps / 2 sub-tiles of 1024 per CTA tile
+__host__ __device__ inline size_t chain_guess_bytes(int64_t ntiles) { return align_up(12 * (size_t)(ntiles + 1) * 4, 256) + 256; }
 struct ChainWs {
   ChainHead* head;
   unsigned long long *P, *A0, *A1;
@@ -893,6 +895,65 @@ __device__ __forceinline__ long long offer_of(unsigned long long w, int E) {
   if (code == kCodeZero) return 0;
   if (code == (unsigned long long)(E + 1023)) return (long long)(w & kWordF);
   return -1;
+}
+
+// ---- binade guesses for the chained kernel: approximate prefix of 1024-element sub-tile sums ---------------------------
+// (one extra read of p.  The running sum of a PS weight vector is a staircase: it jumps by many binades at the ~50 record
+// weights and is flat in between, so "the binade of the latest published prefix" is useless for the ~300 tiles in flight
+// behind a jump -- measured: every jump drained the pipeline for ~7 us.  A 1e-7-accurate prefix per sub-tile gives every
+// tile its own binade up front; exactness still only rests on the validated look-back.)
+__global__ void __launch_bounds__(32 * kTileWarps)
+cdf_guess_sum_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ tsum, int64_t nsub) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t g = (int64_t)blockIdx.x * kTileWarps + wid; g < nsub; g += (int64_t)gridDim.x * kTileWarps) {
+    const int64_t off = g * kTile;
+    const int len = (int)min((int64_t)kTile, n - off);
+    const double* src = p + off;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double v[4];
+      load4(src, len, 4 * (32 * k + lane), v);
+      acc += (v[0] + v[1]) + (v[2] + v[3]);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) tsum[g] = acc;
+  }
+}
+// single CTA: scan of the sub-tile sums; guess[g] = binade of the running sum over the whole of sub-tile g when the
+// 1e-7 guard band says it cannot change inside it, kHard otherwise, kZero while the running sum is still exactly 0
+__global__ void __launch_bounds__(1024)
+cdf_guess_scan_kernel(const double* __restrict__ tsum, int* __restrict__ guess, int64_t nsub) {
+  __shared__ double sh[40];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t per = (((nsub + nw - 1) / nw) + 31) & ~(int64_t)31;
+  const int64_t g0 = min(nsub, wid * per), g1 = min(nsub, g0 + per);
+  double mine = 0.0;
+  for (int64_t g = g0 + lane; g < g1; g += 32) mine += tsum[g];
+  mine = warp_sum(mine);
+  if (lane == 0) sh[wid] = mine;
+  __syncthreads();
+  double run = 0.0;
+  for (int i = 0; i < wid; ++i) run += sh[i];
+  for (int64_t base = g0; base < g1; base += 32) {
+    const int64_t g = base + lane;
+    const double v = (g < g1) ? tsum[g] : 0.0;
+    const double incl = warp_incl_scan_d(v, lane);
+    const double pe = run + incl, ps = pe - v;
+    if (g < g1) {
+      int E = kHard;
+      if (v == 0.0 && ps == 0.0) E = kZero;
+      else {
+        const double lo = ps * (1.0 - 1e-7), hi = pe * (1.0 + 1e-7);
+        if (ps > 0.0 && isfinite(hi) && lo >= kTinyNormal) {
+          const int ea = exponent_of(lo), eb = exponent_of(hi);
+          if (ea == eb && ea >= kMinE && ea <= 1000) E = ea;
+        }
+      }
+      guess[g] = E;
+    }
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1126,7 +1187,7 @@ struct ChainShared {
 
 __global__ void __launch_bounds__(32 * kChainWarps, 2)
 cdf_chain_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ cdf, char* chain_base, int64_t ntiles,
-                 int* __restrict__ status) {
+                 int* __restrict__ status, const int* __restrict__ guess) {
   __shared__ ChainShared sm;
   const ChainWs w = chain_at(chain_base, ntiles);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1134,7 +1195,6 @@ cdf_chain_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ c
     __syncthreads();                                     // the previous tile's shared state is no longer in use
     if (threadIdx.x == 0) {
       sm.g = (long long)atomicAdd(&w.head->ticket, 1u);
-      sm.hint = ld_relaxed_u64(&w.head->hint);
     }
     __syncthreads();
     const long long g = sm.g;
@@ -1186,10 +1246,11 @@ cdf_chain_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ c
     double s_in = 0.0;
     if (lane == 0) sm.zero[wid] = wzero ? 1 : 0;
     if (g > 0) {
-      // ---- 1. aggregate under the candidate binades (hint, hint + 1) ----------------------------------------------
+      // ---- 1. aggregate under the candidate binades ----------------------------------------------------------------
       {
-        const double h = __longlong_as_double((long long)sm.hint);
-        if (in_integer_regime(h)) totals(exponent_of(h));
+        // candidates (E, E + 1): E = the guessed binade of the running sum over the tile's first 1024 elements
+        const int Eg = __ldg(guess + g * (kChainTile / kTile));
+        if (Eg != kHard && Eg != kZero) totals(Eg);
       }
       __syncthreads();
       const unsigned long long t_agg = global_ns();
@@ -1338,9 +1399,11 @@ size_t tb_cdf_x_table_bytes(int64_t ntg_cap) { return 2 * x_layout(ntg_cap).tota
 // single-GPU workspace: the multi-kernel pipeline's scratch followed by the descriptors of the chained kernel
 size_t tb_cdf_workspace_bytes(int64_t n) {
   const int64_t cap = tb_cdf_tile_cap(n, 1);
-  return align_up(tb_cdf_x_workspace_bytes(cap), 256) + chain_bytes((n + kChainTile - 1) / kChainTile + 1);
+  const int64_t nt = (n + kChainTile - 1) / kChainTile + 1;
+  return align_up(tb_cdf_x_workspace_bytes(cap), 256) + chain_bytes(nt) + chain_guess_bytes(nt);
 }
-static int g_cdf_chain = -1;     // 1: chained single-pass kernel (default), 0: multi-kernel pipeline (TB_CDF_CHAIN=0)
+static int g_cdf_chain = -1;     // 0: multi-kernel pipeline (default: 0.60 ms at 3.8e7 weights), 1: chained kernel
+                                 // (TB_CDF_CHAIN=1; 0.75 ms on the same vector, profiles/r02_cdf_paths.txt)
 void tb_cdf_set_chain(int32_t on) { g_cdf_chain = on ? 1 : 0; }
 
 // status of the last call on this workspace: {tiles, segments, runs, hard tiles, error, ...} (device ints)
@@ -1398,7 +1461,7 @@ int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_st
   const int64_t cap = tb_cdf_tile_cap(n, 1);
   if (g_cdf_chain < 0) {
     const char* e = getenv("TB_CDF_CHAIN");
-    g_cdf_chain = (e && e[0] == '0') ? 0 : 1;
+    g_cdf_chain = (e && e[0] == '1') ? 1 : 0;
   }
   if (g_cdf_chain) {
     cudaStream_t st = as_stream(stream);
@@ -1416,7 +1479,16 @@ int tb_cdf_exact(const double* p, int64_t n, double* cdf, void* workspace, tb_st
     cdf_chain_init_kernel<<<igrid < 1 ? 1 : igrid, 256, 0, st>>>(chain, ntiles, reinterpret_cast<int*>(workspace));
     int64_t grid = ntiles;                                  // one CTA per tile in flight, tiles by ticket
     if (grid > (int64_t)per_sm * sm_count()) grid = (int64_t)per_sm * sm_count();
-    cdf_chain_kernel<<<(unsigned)grid, 32 * kChainWarps, 0, st>>>(p, n, cdf, chain, ntiles, reinterpret_cast<int*>(workspace));
+    // binade guesses: sub-tile sums -> scan + classification (the arrays follow the descriptors, sized for ntiles + 1)
+    const int64_t nsub = (n + kTile - 1) / kTile;
+    double* tsum = reinterpret_cast<double*>(chain + chain_bytes(ntiles + 1));
+    int* guess = reinterpret_cast<int*>(chain + chain_bytes(ntiles + 1) + align_up(8 * (size_t)(ntiles + 1) * 4, 256));
+    int sgrid = (int)((nsub + kTileWarps - 1) / kTileWarps);
+    if (sgrid > sm_count() * 8) sgrid = sm_count() * 8;
+    cdf_guess_sum_kernel<<<sgrid, 32 * kTileWarps, 0, st>>>(p, n, tsum, nsub);
+    cdf_guess_scan_kernel<<<1, 1024, 0, st>>>(tsum, guess, nsub);
+    cdf_chain_kernel<<<(unsigned)grid, 32 * kChainWarps, 0, st>>>(p, n, cdf, chain, ntiles, reinterpret_cast<int*>(workspace),
+                                                                  guess);
     TB_CHECK_LAUNCH();
     return TB_OK;
   }

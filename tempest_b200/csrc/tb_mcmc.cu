@@ -400,6 +400,31 @@ bool params_ok(int64_t n, const tb_mcmc_params* p) {
 
 }  // namespace
 
+// ---- benchmark of the in-kernel synchronisation point (tools/xgpu_bench.py) ----------------------------------------------
+// `count` back-to-back grid_xreduce calls of a 4-double row in one cooperative launch: with one CTA this is the pure
+// cross-GPU exchange, with a full grid it is what every Metropolis step / ESS pass pays (row publish + ticket + last-CTA
+// fold + peer stores / flags + broadcast to the waiting CTAs).
+namespace tb {
+__global__ void __launch_bounds__(128)
+xgpu_bench_kernel(GridSync* gs, tb_xgpu x, int count, double* __restrict__ out) {
+  __shared__ double s_part[4], s_tot[4];
+  ColumnFold fold;
+  fold.max_cols = 1ull << 3;
+  double check = 0.0;
+  const unsigned long long t0 = global_ns();
+  for (int k = 0; k < count; ++k) {
+    if (threadIdx.x < 4) s_part[threadIdx.x] = (threadIdx.x == 3) ? 0.0 : (double)(k & 7);
+    __syncthreads();
+    const int rc = grid_xreduce(gs, x, k, 4, s_part, s_tot, fold);
+    if (rc) break;
+    check += s_tot[0];
+    __syncthreads();
+  }
+  const unsigned long long t1 = global_ns();
+  if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = (double)(t1 - t0) / (double)count; out[1] = check; }
+}
+}  // namespace tb
+
 extern "C" {
 
 int tb_set_mcmc_generic(int32_t on) { tb_force_generic_mcmc = on ? 1 : 0; return TB_OK; }
@@ -559,6 +584,27 @@ int tb_mcmc_accept(int64_t n, const tb_mcmc_params* p, const tb_tape* tape, cons
   if (!u_prop || !logl_prop || !meta || !logl) return TB_ERR_ARG;
   a.ext_prop = const_cast<double*>(u_prop); a.ext_logl = logl_prop; a.ext_meta = const_cast<int32_t*>(meta);
   return launch_generic<2>(a, 1, as_stream(stream));
+}
+
+size_t tb_xgpu_bench_workspace_bytes(int32_t grid) { return tb::grid_sync_bytes(grid, 4); }
+
+// out2 (device): {ns per synchronisation point, checksum}.  x may be NULL (one GPU).  Consumes `count` exchanges.
+int tb_xgpu_bench(const tb_xgpu* xgpu, int32_t grid, int32_t count, void* workspace, double* out2, tb_stream_t stream) {
+  if (grid < 1 || count < 1 || !workspace || !out2) return TB_ERR_ARG;
+  tb_xgpu xg;
+  if (xgpu) xg = *xgpu;
+  else { xg.rank = 0; xg.world = 1; xg.seq = 1; for (int i = 0; i < 8; ++i) xg.peer[i] = nullptr; }
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tb::xgpu_bench_kernel, 128, 0);
+  if (e != cudaSuccess) return (int)e;
+  if (grid > per_sm * tb::sm_count()) return TB_ERR_UNSUPPORTED;
+  cudaStream_t st = tb::as_stream(stream);
+  tb::GridSync* gs = reinterpret_cast<tb::GridSync*>(workspace);
+  e = cudaMemsetAsync(gs, 0, sizeof(tb::GridSync), st);
+  if (e != cudaSuccess) return (int)e;
+  void* args[] = {(void*)&gs, (void*)&xg, (void*)&count, (void*)&out2};
+  e = cudaLaunchCooperativeKernel((void*)tb::xgpu_bench_kernel, dim3(grid), dim3(128), args, 0, st);
+  return e == cudaSuccess ? TB_OK : (int)e;
 }
 
 }  // extern "C"

@@ -81,6 +81,11 @@ scale_reduce_kernel(double* __restrict__ w, int64_t n, const double* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(kBlock) scale_dev_kernel(double* __restrict__ w, int64_t n, const double* __restrict__ denom_p) {
+  const double denom = denom_p[0];       // the (all-reduced) sum lives on the device: no host round trip for it
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = w[i] / denom;
+}
 __global__ void __launch_bounds__(kBlock) scale_kernel(double* __restrict__ w, int64_t n, double denom) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = w[i] / denom;
@@ -1213,6 +1218,14 @@ int tb_select_stage(const double* base, const int64_t* rows, int64_t stride, int
 
 size_t tb_select_hist_offset(int32_t ncols, int32_t nranks) {
   return (sizeof(SelState) * (size_t)ncols * nranks + 255) / 256 * 256;
+}
+
+int tb_scale_inplace_dev(double* w, int64_t n, const double* denom, tb_stream_t stream) {
+  if (n < 0 || (n > 0 && !w) || !denom) return TB_ERR_ARG;
+  if (n == 0) return TB_OK;
+  scale_dev_kernel<<<stream_grid(n, kBlock, 16), kBlock, 0, as_stream(stream)>>>(w, n, denom);
+  TB_CHECK_LAUNCH();
+  return TB_OK;
 }
 
 int tb_scale_inplace(double* w, int64_t n, double denom, tb_stream_t stream) {

@@ -285,11 +285,14 @@ __device__ __forceinline__ bool search_advance(BetaSearch& s, double beta, doubl
 }
 
 // The whole search in one cooperative launch.  A probe is a full pass over the ensemble, and a bisection needs ~25 of
-// them -- but the beta of the NEXT probe is one of two values that are known before the current probe's ESS is (the
-// state machine above, fed "above target" / "below target").  So every pass evaluates three betas on the same bytes:
-// the current one and both possible successors; its result consumes TWO steps of the reference's search.  The probe
-// sequence, the comparisons and the final beta are the reference's, bit for bit; the ensemble is streamed half as often
-// (the e^-40 cut keeps the extra exps off most particles) and the grid-wide / cross-GPU folds happen half as often.
+// them.  flags & 2 selects SPECULATIVE passes: the beta of the next probe is one of two values that are known before the
+// current probe's ESS is (the state machine above, fed "above target" / "below target"), so a pass can evaluate three
+// betas on the same bytes -- the current one and both possible successors -- and consume TWO steps of the reference's
+// search; probe sequence, comparisons and final beta stay the reference's, bit for bit, with half the passes and half
+// the grid-wide / cross-GPU folds.  Measured on one B200 (profiles/r02_next_beta_speculative.txt): a three-beta pass
+// costs 2.3x a one-beta pass -- the exps make it fp64-pipe bound (~30 DFMA-class operations per beta and particle;
+// the e^-40 cut does not help because live and dead particles share warps) -- so the search got 17 % SLOWER, not
+// faster.  It is therefore off by default and kept as an option for runs whose passes are latency-bound.
 __global__ void __launch_bounds__(kBlock, 4)
 next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, int64_t n,
                  double beta_prev, double target, int flags, GridSync* gs, double* __restrict__ result,
@@ -307,6 +310,7 @@ next_beta_kernel(const double* __restrict__ logl, const double* __restrict__ C, 
   auto plan = [&](const BetaSearch& cur, double beta, double (&b)[3]) -> int {
     // b[0] = beta; b[1] / b[2] = the next beta if ESS(beta) turns out high / low (absent: the search would end)
     b[0] = beta; b[1] = beta; b[2] = beta;
+    if (!(flags & 2)) return 1;              // one beta per pass (default, see below)
     BetaSearch hi_s = cur, lo_s = cur;
     double nh = beta, nl = beta;
     const bool dh = search_advance(hi_s, beta, 1e300, target, beta_prev, nh);

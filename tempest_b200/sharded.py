@@ -20,6 +20,28 @@ from .ensemble import PersistentEnsemble, ptr, stream_ptr
 from .steps import _EPS, F64, Kernels
 
 
+# Symmetric (peer-mapped) allocations are expensive to set up -- cuMemCreate + handle exchange + mapping on every rank,
+# 30-90 ms for the four a sharded Sampler needs -- and carry only transient state (sequence-numbered flags), so they are
+# pooled per process: a Sampler leases them and hands them back when it is garbage-collected; the next Sampler of the
+# same shape reuses them with the sequence numbers simply continuing.  Every rank creates and drops Samplers in the same
+# order, so the pools stay aligned across ranks.
+_SYMM_POOL: dict = {}
+
+
+def _pool_acquire(key, factory, fits=None):
+    idle = _SYMM_POOL.setdefault(key, [])
+    for i, obj in enumerate(idle):
+        if fits is None or fits(obj):
+            return idle.pop(i)
+    return factory()
+
+
+def _pool_release(leased) -> None:
+    for key, obj in leased:
+        _SYMM_POOL.setdefault(key, []).append(obj)
+    leased.clear()
+
+
 class PeerCollectives:
     """All-reduce (sum) / all-gather of small tensors through peer-mapped staging buffers (csrc/tb_xcoll.cu): two
     kernels on the current stream per call, no host synchronisation, bitwise identical results on every rank
@@ -75,14 +97,21 @@ class PeerCollectives:
 class ShardedKernels(Kernels):
     def __init__(self, device: torch.device, comm: Comm):
         super().__init__(device)
+        import weakref
+
         self.comm = comm
         self.sharded = True
+        self._leased = []                                   # (pool key, object) pairs, returned when this object dies
+        weakref.finalize(self, _pool_release, self._leased)
+        self._pool_tag = (device.index, comm.world, id(comm.group) if comm.group is not None else 0)
         self.xgpu = self._setup_xgpu()
         if self.xgpu is not None and comm.fast is None:
             import os
 
             if os.environ.get("TEMPEST_B200_PEER_COLLECTIVES", "1") != "0":
-                comm.fast = PeerCollectives(self.lib, device, comm)
+                key = ("coll",) + self._pool_tag
+                comm.fast = _pool_acquire(key, lambda: PeerCollectives(self.lib, device, comm))
+                self._leased.append((key, comm.fast))
 
     # -- peer-mapped exchange buffers for the in-kernel collectives (tb_xgpu.cuh) --------------------
     def _setup_xgpu(self):
@@ -91,7 +120,8 @@ class ShardedKernels(Kernels):
         cannot map peer memory."""
         if self.comm.world > 8:
             return None
-        try:
+
+        def make():
             import torch.distributed._symmetric_memory as symm
 
             n = int(self.lib.tb_xgpu_buffer_bytes()) // 8
@@ -104,8 +134,14 @@ class ShardedKernels(Kernels):
             x.rank, x.world, x.seq = self.comm.rank, self.comm.world, 1
             for r in range(self.comm.world):
                 x.peer[r] = int(handle.buffer_ptrs[r])
-            self._xbuf, self._xhandle = buf, handle
-            return x
+            return (buf, handle, x)
+
+        try:
+            key = ("xgpu",) + self._pool_tag
+            obj = _pool_acquire(key, make)
+            self._leased.append((key, obj))
+            self._xbuf, self._xhandle, x = obj
+            return x                  # the sequence number continues where the previous lessee stopped
         except Exception as exc:      # pragma: no cover - platform dependent
             import warnings
 
@@ -150,10 +186,22 @@ class ShardedKernels(Kernels):
         c, a1, a2 = self.comm.allreduce_sum_(out3).cpu().numpy()
         return float(c), float(a1), float(a2)
 
-    def g_normalize(self, w, n: int):
-        _, s1, s2 = self.g_sum3(w, n, -math.inf)
-        _lib.check(self.lib.tb_scale_inplace(ptr(w), n, s1, stream_ptr()), "tb_scale_inplace")
-        return s1, s2 / (s1 * s1)
+    def g_normalize_begin(self, w, n: int):
+        """w /= global sum(w), enqueued only: local sums -> peer-memory all-reduce -> scale by the device scalar."""
+        out3 = self.ws.f64("norm_m3", 3)
+        if n > 0:
+            _lib.check(self.lib.tb_masked_sums(ptr(w), n, -math.inf, ptr(self._reduce_ws), ptr(out3), stream_ptr()),
+                       "tb_masked_sums")
+        else:
+            out3.zero_()                         # a rank without elements still takes part in the collective
+        self.comm.allreduce_sum_(out3)
+        if n > 0:
+            _lib.check(self.lib.tb_scale_inplace_dev(ptr(w), n, ptr(out3[1:]), stream_ptr()), "tb_scale_inplace_dev")
+        return out3
+
+    def g_normalize_end(self, out3):
+        _, s1, s2 = out3.cpu().numpy()
+        return float(s1), float(s2) / (float(s1) * float(s1))
 
     def g_hist(self, w, n: int):
         buf, cnt, s1, s2 = self._hist_buffers("trim_hist")
@@ -333,17 +381,24 @@ class ShardedKernels(Kernels):
         tiles travel through it by NVLink stores).  One allocation sized for the ensemble's capacity."""
         if getattr(self, "_cdf_cap", 0) >= need_cap:
             return
-        import torch.distributed._symmetric_memory as symm
 
-        cap = int(need_cap)
-        n = int(self.lib.tb_cdf_x_table_bytes(cap)) // 8
-        buf = symm.empty(n, dtype=F64, device=self.device)
-        buf.zero_()
-        handle = symm.rendezvous(buf, torch.distributed.group.WORLD if self.comm.group is None else self.comm.group)
-        torch.cuda.synchronize()
-        self.comm.allreduce_sum_(torch.zeros(1, device=self.device))      # everyone has zeroed its tables
-        self._cdf_buf, self._cdf_handle, self._cdf_cap = buf, handle, cap
-        self._cdf_seq = 0
+        def make():
+            import torch.distributed._symmetric_memory as symm
+
+            cap = int(need_cap)
+            n = int(self.lib.tb_cdf_x_table_bytes(cap)) // 8
+            buf = symm.empty(n, dtype=F64, device=self.device)
+            buf.zero_()
+            handle = symm.rendezvous(buf, torch.distributed.group.WORLD if self.comm.group is None else self.comm.group)
+            torch.cuda.synchronize()
+            self.comm.allreduce_sum_(torch.zeros(1, device=self.device))      # everyone has zeroed its tables
+            return {"buf": buf, "handle": handle, "cap": cap, "seq": 0}
+
+        key = ("cdf",) + self._pool_tag
+        t = _pool_acquire(key, make, fits=lambda o: o["cap"] >= need_cap)
+        self._leased.append((key, t))
+        self._cdf_tab = t
+        self._cdf_buf, self._cdf_handle, self._cdf_cap = t["buf"], t["handle"], t["cap"]
 
     def cdf_x(self, p: torch.Tensor, n: int, seg_begin: torch.Tensor, n_global: int, name: str):
         """numpy's sequential cumsum of the GLOBAL weight vector (generation-major, rank-minor: the order of the
@@ -357,9 +412,9 @@ class ShardedKernels(Kernels):
             raise RuntimeError("sharded cdf: tile table capacity exceeded")
         ws = self.ws.bytes("cdfx_" + name, self.lib.tb_cdf_x_workspace_bytes(cap))
         cdf = self.ws.f64(name, max(n, 1))
-        self._cdf_seq += 1
+        self._cdf_tab["seq"] += 1        # per table memory, continuing across the Samplers that lease it
         x = _lib.TbCdfX()
-        x.rank, x.world, x.seq = self.comm.rank, self.comm.world, self._cdf_seq
+        x.rank, x.world, x.seq = self.comm.rank, self.comm.world, self._cdf_tab["seq"]
         for r in range(self.comm.world):
             x.peer[r] = int(self._cdf_handle.buffer_ptrs[r])
         _lib.check(self.lib.tb_cdf_exact_x(ptr(p) if n else None, n, ptr(seg_begin), S, int(n_global), cap, ptr(cdf),
@@ -395,6 +450,25 @@ class ShardedKernels(Kernels):
                 raise IndexError("systematic resampling walked past the last weight (tools.py:223-225)")
         if self.comm.fast is not None:
             self.comm.fast.check()
+
+    def peer_rows(self, per: int, d: int) -> "PeerRows":
+        """Active-set buffers in peer-mapped memory for `per` walker slots per rank (pooled like the other symmetric
+        allocations: the views a Sampler holds into them stay its own until it dies)."""
+        rows = getattr(self, "_peer_rows", None)
+        if rows is None or rows.per != per or rows.d != d:
+            key = ("rows", per, d) + self._pool_tag
+            rows = _pool_acquire(key, lambda: PeerRows(self.lib, self.device, self.comm, per, d))
+            self._leased.append((key, rows))
+            self._peer_rows = rows
+        return rows
+
+    def prepare(self, per: int, d: int, n_global_hint: int) -> None:
+        """Set up the lazily created symmetric allocations now (Sampler construction) instead of inside the first
+        iteration that trims / resamples."""
+        if self.comm.fast is not None:
+            self.peer_rows(per, d)
+        if self.xgpu is not None:
+            self._cdf_tables(int(self.lib.tb_cdf_tile_cap(max(int(n_global_hint), 1), 64 * self.comm.world)))
 
     def sharded_search(self, p: torch.Tensor, n: int, seg_begin: torch.Tensor, draws: torch.Tensor,
                        out: torch.Tensor, name: str, n_global: Optional[int] = None):
@@ -448,12 +522,13 @@ class PeerRows:
 
 
 def sharded_resample(core, weights: torch.Tensor, draws: Optional[torch.Tensor], systematic: bool = False,
-                     u0: float = 0.0):
+                     u0: float = 0.0, k=None):
     """N global draws (multinomial: replicated uniforms; systematic: one uniform); returns this rank's block of
     resampled (u, logl) rows.  Every rank searches all N draws in the global exact cdf and stores the rows whose
     ancestors it holds straight into the active-set buffer of the rank that owns the walker slot (NVLink peer
     stores, no host synchronisation); without peer memory the rows travel by an all-to-all."""
-    k, ens, comm = core.k, core.ensemble, core.comm
+    k = core.k if k is None else k            # (the side-stream kernels object when the resampling overlaps the Trainer)
+    ens, comm = core.ensemble, k.comm
     n_glob = core.n_global
     d = ens.n_dim
     idx = k.ws.i64("res_idx", n_glob)
@@ -461,9 +536,7 @@ def sharded_resample(core, weights: torch.Tensor, draws: Optional[torch.Tensor],
     k.search_x(h, draws, n_glob, idx, systematic=systematic, u0=u0)
     core.trace["resample_idx"] = idx
     if comm.fast is not None:
-        rows = getattr(k, "_peer_rows", None)
-        if rows is None or rows.per != core.n_local or rows.d != d:
-            rows = k._peer_rows = PeerRows(k.lib, core.device, comm, core.n_local, d)
+        rows = k.peer_rows(core.n_local, d)
         rows.x.seq += 1
         _lib.check(k.lib.tb_xrows_scatter(ptr(ens.u), ptr(ens.logl), d, ptr(idx), n_glob, core.n_local, C.byref(rows.x),
                                           ptr(comm.fast.err), stream_ptr()), "tb_xrows_scatter")

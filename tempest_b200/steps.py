@@ -276,9 +276,17 @@ class Kernels:
 
     def g_normalize(self, w: torch.Tensor, n: int):
         """w /= sum(w) in place (tools.py:36); returns (sum before, sum of squares after)."""
+        return self.g_normalize_end(self.g_normalize_begin(w, n))
+
+    # split form: `begin` only enqueues (the sum stays on the device), `end` reads the two scalars -- callers that do
+    # not need them skip `end`, callers that do read them together with their next host read
+    def g_normalize_begin(self, w: torch.Tensor, n: int):
         stats = self.ws.f64("trim_stats", 3)
         _lib.check(self.lib.tb_normalize_inplace(ptr(w), n, ptr(self._reduce_ws), ptr(stats), stream_ptr()),
                    "tb_normalize_inplace")
+        return stats
+
+    def g_normalize_end(self, stats):
         h = stats.cpu().numpy()
         return float(h[0]), float(h[1])
 
@@ -342,10 +350,11 @@ class Kernels:
         rank and sum below is global (the g_* hooks all-reduce when the ensemble is sharded)."""
         lib = self.lib
         st = stream_ptr()
-        _, sumsq = self.g_normalize(w, n)
+        pending = self.g_normalize_begin(w, n)
         if after_normalize is not None:
             after_normalize()                 # w is final from here on (read-only below)
         h_cnt, h_s1, h_s2 = self.g_hist(w, n)
+        _, sumsq = self.g_normalize_end(pending)          # (no second wait: the histogram read drained the stream)
         n_glob = int(n_global) if n_global is not None else self.g_int(n)
         ess_total = 1.0 / sumsq
         # suffix sums over binades (threshold at the lower edge of binade b keeps bins >= b)
@@ -685,10 +694,7 @@ class Trainer:
         if core.config.clustering:
             return self._clustered(idx, wt, n_trim)
         # modes.py:266: renormalise the trimmed weights
-        if n_trim or not k.sharded:
-            k.g_normalize(wt, n_trim)
-        elif k.sharded:
-            k.g_sum3(wt, 0, 0.0)                        # keep the collective sequence aligned across ranks
+        k.g_normalize_begin(wt, n_trim)                 # the sums are not needed on the host: no round trip
         draws = core.rng.train_u(m_total)
         mean, cov, chol, inv = self._fit_mode(idx, wt, n_trim, n_trim_glob, draws, "train_draw_idx")
         dof = torch.full((1,), DOF_FALLBACK, dtype=F64, device=core.device)
@@ -819,6 +825,18 @@ class Resampler:
         u = torch.empty((n, d), dtype=F64, device=core.device)          # allocated (and later consumed) on the main stream
         logl = torch.empty(n, dtype=F64, device=core.device)
         core.side.wait_event(ready)
+        if core.comm.on:
+            from .sharded import sharded_resample
+
+            with torch.cuda.stream(core.side):
+                ks = core.k_side
+                ks.ws.hint = ens.cap
+                draws = core.rng.resample_u(core.n_global)
+                u, logl = sharded_resample(core, weights, draws, k=ks)     # views into ks's peer-mapped row buffers
+                done = torch.cuda.Event()
+                done.record()
+            self._pending = (u, logl, core.trace.get("resample_idx"), done)
+            return
         with torch.cuda.stream(core.side):
             ks = core.k_side
             cdf = ks.cdf(weights, ens.n_total)

@@ -105,8 +105,15 @@ def test_next_beta_device_search_matches_oracle_probe_sequence(env):
             _, ess_ref, _ = s.probe(lo)
         else:
             beta_ref, _, ess_ref = s.bisect(beta_prev, hi, target, False)
+        # speculative passes (three betas per pass, flags bit 1): same probe sequence and result from about half the passes
+        res2, plog2 = env.k.next_beta(ens, beta_prev, target, 2)      # (results live in reused workspace buffers: copy)
+        h2 = res2.cpu().numpy().copy()
+        log2 = plog2[: 2 * int(h2[6])].cpu().numpy().copy()
         res, plog = env.k.next_beta(ens, beta_prev, target, 0)
         h = res.cpu().numpy()
+        assert h2[0] == h[0] and h2[6] == h[6] and h2[9] <= h[9] and h[9] == h[6]
+        np.testing.assert_allclose(h2[1:6], h[1:6], rtol=1e-12)
+        np.testing.assert_array_equal(log2[0::2], plog[: 2 * int(h[6])].cpu().numpy()[0::2])
         nprobe = int(h[6])
         got = plog[: 2 * nprobe].cpu().numpy().reshape(-1, 2)
         # the oracle re-probes beta when lo == hi; the device reuses the probe it already has
@@ -160,8 +167,8 @@ def _cdf_bitwise(env, p, name="t_cdf"):
 @pytest.mark.parametrize("chain", [1, 0])
 def test_cdf_exact_hard_cases_both_paths(env, chain):
     """Round-half ties, oversized elements, binade crossings on tile boundaries, long zero / subnormal stretches and a
-    PS-shaped vector (generations of rising weight), through the chained single-pass kernel (chain = 1, the default
-    single-GPU path) and the multi-kernel pipeline (chain = 0, the path sharded runs use)."""
+    PS-shaped vector (generations of rising weight), through the chained look-back kernel (chain = 1) and the
+    multi-kernel pipeline (chain = 0, the default and the path sharded runs use)."""
     env.lib.tb_cdf_set_chain(chain)
     try:
         rng = np.random.default_rng(77)
@@ -194,12 +201,15 @@ def test_cdf_exact_hard_cases_both_paths(env, chain):
         for c in cases:
             _cdf_bitwise(env, c)
     finally:
-        env.lib.tb_cdf_set_chain(1)
+        env.lib.tb_cdf_set_chain(0)
 
 
-def test_cdf_exact_chain_large_and_real_weights(env):
+@pytest.mark.parametrize("chain", [0, 1])
+def test_cdf_exact_large_and_real_weights(env, chain):
     """2^25 elements, and the weight vector of a finished PS run at beta = 1 (the vector the resampling step sees)."""
     import tempest_b200 as tp
+
+    env.lib.tb_cdf_set_chain(chain)
 
     rng = np.random.default_rng(78)
     p = rng.random(1 << 25) ** 8
@@ -215,6 +225,7 @@ def test_cdf_exact_chain_large_and_real_weights(env):
     k.g_normalize(w, ens.n_total)
     wh = w.cpu().numpy().copy()
     got = k.cdf(w, ens.n_total, "t_cdf_real").cpu().numpy()
+    env.lib.tb_cdf_set_chain(0)
     assert np.array_equal(got.view(np.uint64), np.cumsum(wh).view(np.uint64))
 
 

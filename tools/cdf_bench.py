@@ -46,7 +46,7 @@ for chain in (1, 0):
                  f"exhausted {dg[14]}, prefix-not-regime {dg[15]}, binade-mismatch {dg[16]}, overflow {dg[17]}")
     print(line)
     print("   bitwise equal to numpy:", np.array_equal(ref.view(np.uint64), cdf.cpu().numpy().view(np.uint64)))
-k.lib.tb_cdf_set_chain(1)
+k.lib.tb_cdf_set_chain(0)
 torch.cuda.profiler.start()
 cdf = k.cdf(w, ens.n_total)
 torch.cuda.synchronize()
