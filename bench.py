@@ -461,7 +461,7 @@ def main():
     nb_ms, nb_work, nb_n = hot.get("next_beta", (0.0, 0.0, 0))
     if nb_ms > 0:
         others["next_beta_kernel (in situ, all launches of the timed region)"] = {
-            "ms": nb_ms / nb_n, "launches": nb_n, "bytes_per_particle_probe": 16,
+            "ms": nb_ms / nb_n, "launches": nb_n, "bytes_per_particle_pass": 16,
             "gbs": 16.0 * nb_work / nb_ms / 1e6, "share_of_timed_region": nb_ms / ms}
     probe_ms = cuda_ms(lambda i=0: Kernels.probe(core2.k, ens, 0.3 + 0.01 * i))     # local kernel only
     others["probe_kernel"] = {"ms": probe_ms, "bytes_per_particle": 16, "gbs": 16.0 * n_hist / probe_ms / 1e6,
@@ -476,7 +476,14 @@ def main():
     others["weights_kernel"] = {"ms": ms_w, "bytes_per_particle": 24, "gbs": 24.0 * n_hist / ms_w / 1e6}
     ms_c = cuda_ms(lambda i=0: core2.k.cdf(wbuf, n_hist), reps=10)
     others["cdf_exact"] = {"ms": ms_c, "bytes_per_particle": 16, "gbs": 16.0 * n_hist / ms_c / 1e6,
-                           "note": "algorithmic bytes: read w, write cdf (SURVEY 8d)"}
+                           "note": "multi-kernel pipeline (default); algorithmic bytes: read w, write cdf (SURVEY 8d)"}
+    if world == 1:
+        lib.tb_cdf_set_chain(1)
+        ms_cc = cuda_ms(lambda i=0: core2.k.cdf(wbuf, n_hist), reps=10)
+        lib.tb_cdf_set_chain(0)
+        others["cdf_exact (chained look-back kernel, option)"] = {
+            "ms": ms_cc, "bytes_per_particle": 16, "gbs": 16.0 * n_hist / ms_cc / 1e6,
+            "note": "guess pass + one chained kernel; stalls at the ~55 multi-binade jumps of the running sum (DESIGN 4)"}
     if world == 1:
         ms_n = cuda_ms(lambda i=0: core2.k.next_beta(ens, 0.5, 2.0 * n_particles, 0), reps=5)
         npr = float(core2.k.ws.f64("nb_res", 16)[6].item())

@@ -135,10 +135,24 @@ class SamplerCore:
     def warmup_regime(self) -> bool:
         return self.ensemble.all_warmup()
 
+    def zero_assignments(self, n: int) -> np.ndarray:
+        """The all-zero label vector of an unclustered iteration (resample.py:71; one shared read-only array instead of
+        a fresh 8 MB fill per iteration)."""
+        z = getattr(self, "_zero_assign", None)
+        if z is None or z.shape[0] != n:
+            z = np.zeros(n, dtype=int)
+            z.flags.writeable = False
+            self._zero_assign = z
+        return z
+
     def generation_bounds(self) -> torch.Tensor:
         """Local start positions [T+1] of every stored generation in this rank's history shard."""
-        b = np.concatenate([[0], np.cumsum(self.ensemble.gen_n_local)]).astype(np.int64)
-        return torch.as_tensor(b).to(self.device)
+        key = (len(self.ensemble.gen_n_local), self.ensemble.n_total)
+        cached = getattr(self, "_gen_bounds", None)
+        if cached is None or cached[0] != key:          # (two callers per iteration; one host -> device copy)
+            b = np.concatenate([[0], np.cumsum(self.ensemble.gen_n_local)]).astype(np.int64)
+            cached = self._gen_bounds = (key, torch.as_tensor(b).to(self.device))
+        return cached[1]
 
     def weights_buffer(self) -> torch.Tensor:
         n = self.ensemble.n_total

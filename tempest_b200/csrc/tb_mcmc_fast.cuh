@@ -18,10 +18,11 @@ namespace tb {
 // uniform instead of gamma_mt / normals_fixed / accept_uniform): the parity tests therefore run the
 // production arithmetic, including the constant-memory single-mode variant and the compile-time likelihood.
 
-// resident CTAs (of kRunWarps warps) per SM the register allocation is held to
-// (measured at D = 10 in round 1: 28 one-warp CTAs / 72 registers beat 24 / 80)
+// Two CTAs per SM; warps per CTA such that the register allocation is held to 72 / 128 / 168 registers
+// (measured at D = 10 in round 1: 28 warps / 72 registers beat 24 / 80).  Few, large CTAs keep the per-step grid
+// synchronisation short: 296 rows to fold instead of 1036 (tools/xgpu_bench.py: 4.8 vs 7.2 us per step).
 template <int D>
-constexpr int mcmc_min_ctas() { return (D <= 10 ? 7 : (D <= 12 ? 4 : 3)); }
+constexpr int mcmc_warps() { return (D <= 10 ? 14 : (D <= 12 ? 8 : 6)); }
 
 // Single-mode runs (K = 1, the clustering=False headline path) read the mode statistics and the prior box
 // from constant memory: the operands fold into the DFMAs, so the ~3 D^2/2 shared-memory loads per
@@ -36,7 +37,7 @@ template <int D, bool TPCN, bool TAPE, bool KONE, int LIKE>
 struct FastBody {
   static constexpr bool kSingleMode = KONE;
   static constexpr bool kDeferred = true;       // run_steps drives pass() with the deferred-redraw list
-  static constexpr int kWarps = 4;
+  static constexpr int kWarps = mcmc_warps<D>();
   static constexpr int CM_CHOL = D, CM_INV = D + D * D, CM_PRIOR = D + 2 * D * D, CM_DOF = D + 2 * D * D + 2 * D;
 
   // CTA area (multi-mode variant only): mean[K][D], chol[K][D][D], inv[K][D][D] (symmetric form: off-diagonals
@@ -275,7 +276,7 @@ struct FastBody {
 };
 
 template <int D, bool TPCN, bool TAPE, bool KONE, int LIKE>
-__global__ void __launch_bounds__(128, mcmc_min_ctas<D>())
+__global__ void __launch_bounds__(32 * mcmc_warps<D>(), 2)
 mcmc_run_fast(const StepArgs a) {
   extern __shared__ double dyn_smem[];
   run_steps<FastBody<D, TPCN, TAPE, KONE, LIKE>>(a, dyn_smem);

@@ -8,7 +8,7 @@
 namespace tb {
 
 constexpr int kMcmcBlock = 128;      // walkers per CTA of the per-launch runtime-dimension kernel (split step)
-constexpr int kRunWarpsMax = 8;      // upper bound on BODY::kWarps (warps per CTA of the persistent kernels)
+constexpr int kRunWarpsMax = 16;     // upper bound on BODY::kWarps (warps per CTA of the persistent kernels)
 constexpr int kMaxModes = 64;
 constexpr int kMaxAttempts = 100000;
 constexpr int kDeferCap = 64;        // deferred-redraw list entries per warp (flushed whenever 32 are waiting)

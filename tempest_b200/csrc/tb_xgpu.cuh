@@ -101,6 +101,8 @@ __device__ __noinline__ int grid_xreduce(GridSync* gs, const tb_xgpu& x, int k, 
     __threadfence();
     __syncwarp();
     if (lane == 0) {
+      // (a two-level arrival -- 32 group counters, then one -- was measured SLOWER: +1 us at every grid size; the extra
+      //  fence + atomic round trip costs more than a thousand arrivals on one L2 counter do)
       const unsigned int old = atomicAdd(&gs->arrive, 1u);
       s_last = (old == (unsigned)(k + 1) * (unsigned)nb - 1u) ? 1 : 0;     // last CTA of this GPU for sync point k
       s_bad = 0;
@@ -164,11 +166,11 @@ struct ColumnFold {
   __device__ void rows(const double* rows, int nb, int W, double* tot) const {
     __shared__ double s_w[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5, B = blockDim.x;
-    if (W <= 4 && nw <= 8) {
+    if (W <= 4 && nw <= 16) {
       // narrow rows (single-mode runs: sum alpha, accepted, proposals, error): every thread folds whole rows, so the
       // columns share one pass over the rows, one warp reduction each and ONE barrier (the per-column form below
       // costs two barriers per column on the critical path of every Metropolis step)
-      __shared__ double s_wc[8][4];
+      __shared__ double s_wc[16][4];
       double v[4][2];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {

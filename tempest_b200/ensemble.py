@@ -33,7 +33,14 @@ HISTORY_STATE_KEYS = frozenset({
     "acceptance", "beta"})  # state_manager.py:26-42
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> C.c_void_p:
+    """cudaStream_t of torch's current stream on the current device (every C-ABI call takes it).  The raw accessor is
+    ~50x cheaper than building a torch.cuda.Stream object -- at ~2 000 calls per run that was 6 % of the host path."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -853,7 +853,7 @@ class Resampler:
         st = core.state
         n = core.n_local
         if float(st.raw("beta")) == 0.0:               # resample.py:69-72
-            st.set_current("assignments", np.zeros(n, dtype=int))
+            st.set_current("assignments", core.zero_assignments(n))
             return
         ens = core.ensemble
         k = core.k
@@ -863,7 +863,7 @@ class Resampler:
             torch.cuda.current_stream().wait_event(done)
             core.trace["resample_idx"] = idx
             core.assign = None
-            st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": core.zero_assignments(n)})
             return
         if k.sharded:
             from .sharded import sharded_resample
@@ -872,7 +872,7 @@ class Resampler:
                 u, logl = sharded_resample(core, weights, core.rng.resample_u(core.n_global))
             else:
                 u, logl = sharded_resample(core, weights, None, systematic=True, u0=core.rng.resample_u0())
-            st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": core.zero_assignments(n)})
             return
         cdf = k.cdf(weights, ens.n_total)
         idx = k.ws.i64("res_idx", n)
@@ -892,7 +892,7 @@ class Resampler:
             st.update_current({"u": u, "x": None, "logl": logl, "assignments": assign})
         else:
             core.assign = None
-            st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int)})
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": core.zero_assignments(n)})
 
 
 class Mutator:
@@ -954,7 +954,7 @@ class Mutator:
             else:
                 _lib.check(lib.tb_prior_draw(n, C.byref(params), ptr(tape_u), ptr(u), None, ptr(logl), sp),
                            "tb_prior_draw")
-            st.update_current({"u": u, "x": None, "logl": logl, "assignments": np.zeros(n, dtype=int),
+            st.update_current({"u": u, "x": None, "logl": logl, "assignments": core.zero_assignments(n),
                                "calls": st.raw("calls") + core.n_global, "steps": 1, "acceptance": 1.0,
                                "efficiency": 1.0})
             bad = torch.isinf(logl)
