@@ -513,6 +513,7 @@ class Reweighter:
         self.ess_ratio = cfg.ess_ratio
         self.volume_variation = cfg.volume_variation
         self.device_search = True     # tb_next_beta (one launch) vs host-driven probes
+        self.SPECULATIVE_MAX = 4 << 20  # particles in this rank's history below which passes evaluate three betas
         self.probe_log: List[Tuple[float, float]] = []
 
     # one probe: returns (ess, metric) and leaves (m, S1, ...) in core.k.probe_out
@@ -646,6 +647,11 @@ class Reweighter:
                 out = k.probe(ens, beta_prev)
                 return beta_prev, ess0, out
             flags = 1
+        if ens.n_total <= self.SPECULATIVE_MAX:
+            # short (local) history: a pass is latency-bound (block merges + synchronisation point >> streaming time), so
+            # evaluating the current beta and both possible successors per pass halves the passes for free; on long
+            # histories the three-beta pass is fp64-bound and slower (profiles/r02_next_beta_speculative.txt)
+            flags |= 2
         timing = core.kernel_timing
         if timing is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
