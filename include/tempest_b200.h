@@ -238,6 +238,13 @@ int tb_bucket_offsets(int32_t d, int64_t* out4);
 int tb_bucket_stage(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
                     int64_t rank_lo, int32_t same, double lo_value, double hi_value, int32_t unit_map,
                     int32_t stage, void* workspace, double* out, int32_t* overflow, tb_stream_t stream);
+/* Sharded runs, between stage 2 and stage 3: concatenate the all-gathered candidate lists of the ranks
+ * (gsel int32[world][d][2] = {count, overflow} of every rank's stage 2, gval / gmul [world][d][capx] = the first capx
+ * candidate slots of every rank) into this rank's candidate arrays in rank order and set the global counts; a count
+ * above capx, an overflow on any rank or more than 65 536 candidates in total raise the overflow flag stage 3 reports.
+ * No count visits the host. */
+int tb_bucket_merge(const int32_t* gsel, const double* gval, const uint32_t* gmul, int32_t world, int32_t d, int32_t capx,
+                    void* workspace, tb_stream_t stream);
 int tb_unit_median_pair(const double* u, const int64_t* rows, const int32_t* mult, int64_t n, int32_t d,
                         int64_t rank_lo, void* workspace, double* out, int32_t* overflow,
                         tb_stream_t stream);

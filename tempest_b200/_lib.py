@@ -135,6 +135,7 @@ SIGNATURES = {
     "tb_unit_median_workspace_bytes": (SIZE, [c_i32]),
     "tb_bucket_offsets": (c_i32, [c_i32, PTR]),
     "tb_bucket_stage": (c_i32, [PTR, PTR, PTR, c_i64, c_i32, c_i64, c_i32, c_f64, c_f64, c_i32, c_i32, PTR, PTR, PTR, PTR]),
+    "tb_bucket_merge": (c_i32, [PTR, PTR, PTR, c_i32, c_i32, c_i32, PTR, PTR]),
     "tb_unit_median_pair": (c_i32, [PTR, PTR, PTR, c_i64, c_i32, c_i64, PTR, PTR, PTR, PTR]),
     "tb_bucket_select_pair": (c_i32, [PTR, c_i64, c_i64, c_i32, c_f64, c_f64, c_i32, PTR, PTR, PTR, PTR]),
     "tb_count_indices": (c_i32, [PTR, c_i64, PTR, c_i64, PTR]),
@@ -194,7 +195,7 @@ KERNELS_PER_CALL = {
     "tb_binade_hist": 1, "tb_subbin_hist": 1, "tb_masked_sums": 1, "tb_compact_ge": 3, "tb_select_ranks": 14, "tb_count_indices": 1,
     "tb_counted_moments": 2, "tb_prior_draw": 1, "tb_transform": 1, "tb_mcmc_begin": 2,
     "tb_mcmc_steps": 1, "tb_debug_variates": 1, "tb_fp64_peak_run": 1, "tb_xrows_scatter": 2, "tb_vv_regularise": 1, "tb_vv_finish": 1, "tb_xcoll_allreduce_sum": 2, "tb_xcoll_allgather": 2, "tb_philox_uniform": 1, "tb_search_right_sharded": 1,
-    "tb_scale_inplace": 1, "tb_scale_inplace_dev": 1, "tb_select_stage": 1, "tb_select_pair": 11, "tb_unit_median_pair": 4, "tb_bucket_select_pair": 4, "tb_bucket_stage": 1, "tb_next_beta_x": 1, "tb_moments_partial": 2, "tb_mcmc_update": 1,
+    "tb_scale_inplace": 1, "tb_scale_inplace_dev": 1, "tb_select_stage": 1, "tb_select_pair": 11, "tb_unit_median_pair": 4, "tb_bucket_select_pair": 4, "tb_bucket_stage": 1, "tb_bucket_merge": 1, "tb_next_beta_x": 1, "tb_moments_partial": 2, "tb_mcmc_update": 1,
     "tb_search_right_guided": 2, "tb_search_right_sharded_guided": 2, "tb_mcmc_propose": 1, "tb_mcmc_accept": 1, "tb_kpp_prob": 1, "tb_kpp_pick": 1, "tb_gmm_init": lambda args: 4 + 2 * int(args[5]),
     "tb_gmm_em": lambda args: int(args[13]) * (3 + 2 * int(args[5])), "tb_gmm_bound": 1, "tb_gmm_prepare": 1,
     "tb_gmm_predict": 1, "tb_col_minmax": 1, "tb_gather_normalised": 1, "tb_take": 1, "tb_split_by_label": 3,

@@ -545,6 +545,42 @@ med_small_kernel(const MedSel* __restrict__ sel, const double* __restrict__ cval
   }
 }
 
+// Sharded candidate merge: every rank compacted the candidates of the selected bucket(s) of ITS rows; the all-gathered
+// lists (a fixed `capx` slots per column and rank, so no count has to visit the host first) are concatenated in rank
+// order into this rank's candidate arrays and the global count is set -- the exact in-block select then runs on
+// identical input on every rank.  One CTA per column.
+__global__ void __launch_bounds__(256)
+med_merge_kernel(const int* __restrict__ gsel /* [G][d][2]: count, overflow */, const double* __restrict__ gval,
+                 const unsigned int* __restrict__ gmul, int G, int d, int capx, MedSel* __restrict__ sel,
+                 double* __restrict__ cval, unsigned int* __restrict__ cmul) {
+  __shared__ int off[64 + 1];
+  const int c = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int total = 0, ovf = 0;
+    for (int r = 0; r < G; ++r) {
+      int cnt = gsel[((size_t)r * d + c) * 2];
+      if (gsel[((size_t)r * d + c) * 2 + 1] != 0 || cnt > capx || cnt < 0) { ovf = 1; cnt = 0; }
+      off[r] = total;
+      total += cnt;
+    }
+    off[G] = total;
+    if (total > kMedCap) { ovf = 1; total = 0; }
+    sel[c].count = (unsigned int)total;
+    sel[c].overflow = ovf;
+  }
+  __syncthreads();
+  if (sel[c].overflow) return;
+  for (int r = 0; r < G; ++r) {
+    const int base = off[r], cnt = off[r + 1] - off[r];
+    const double* sv = gval + ((size_t)r * d + c) * capx;
+    const unsigned int* sm = gmul + ((size_t)r * d + c) * capx;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      cval[(size_t)c * kMedCap + base + i] = sv[i];
+      cmul[(size_t)c * kMedCap + base + i] = sm[i];
+    }
+  }
+}
+
 // ---- multiplicities ---------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock)
 count_indices_kernel(const int64_t* __restrict__ idx, int64_t m, int* __restrict__ counts) {
@@ -1139,6 +1175,19 @@ int tb_bucket_stage(const double* u, const int64_t* rows, const int32_t* mult, i
     cudaMemsetAsync(overflow, 0, sizeof(int32_t), st);
     med_small_kernel<<<d, 1024, 0, st>>>(sel, cval, cmul, out, overflow, same);
   }
+  TB_CHECK_LAUNCH();
+  return TB_OK;
+}
+
+int tb_bucket_merge(const int32_t* gsel, const double* gval, const uint32_t* gmul, int32_t world, int32_t d, int32_t capx,
+                    void* workspace, tb_stream_t stream) {
+  if (!gsel || !gval || !gmul || world < 1 || world > 64 || d <= 0 || d > 4096 || capx < 1 || capx > kMedCap || !workspace)
+    return TB_ERR_ARG;
+  int64_t off[4];
+  tb_bucket_offsets(d, off);
+  char* p = (char*)workspace;
+  med_merge_kernel<<<d, 256, 0, as_stream(stream)>>>(gsel, gval, gmul, world, d, capx, (MedSel*)(p + off[1]),
+                                                      (double*)(p + off[2]), (unsigned int*)(p + off[3]));
   TB_CHECK_LAUNCH();
   return TB_OK;
 }

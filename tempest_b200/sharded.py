@@ -95,6 +95,7 @@ class PeerCollectives:
 
 
 class ShardedKernels(Kernels):
+    BUCKET_SLOTS = 1024      # candidate slots per column and rank gathered by the sharded bucket select
     def __init__(self, device: torch.device, comm: Comm):
         super().__init__(device)
         import weakref
@@ -255,28 +256,17 @@ class ShardedKernels(Kernels):
             self.comm.allreduce_sum_(bws[o0: o0 + 4 * d * cap].view(torch.int32))
         stage(1)
         stage(2)
+        # merge the ranks' candidate lists on the device: a fixed number of slots per column and rank is gathered, so no
+        # count has to visit the host before the exact select (one read -- the overflow flag -- per call instead of two
+        # reads and a dozen eager tensor ops; a column with more candidates than slots takes the fallback of the caller)
+        capx = self.BUCKET_SLOTS
         sel = bws[o1: o1 + 24 * d].view(torch.int32).reshape(d, 6)
-        allc_dev = self.comm.allgather(sel[:, 4:6].contiguous())                  # [G, d, (count, overflow)]
-        allc = allc_dev.cpu().numpy()
-        counts = allc[:, :, 0].astype(np.int64)
-        totals = counts.sum(axis=0)
-        if allc[:, :, 1].any() or (totals > cap).any():
-            return False
-        maxc = int(counts.max())
-        if maxc > 0:
-            cval = bws[o2: o2 + 8 * d * cap].view(F64).reshape(d, cap)
-            cmul = bws[o3: o3 + 4 * d * cap].view(torch.int32).reshape(d, cap)
-            gv = self.comm.allgather(cval[:, :maxc].contiguous())                 # [G, d, maxc]
-            gm = self.comm.allgather(cmul[:, :maxc].contiguous())
-            # merge on the device: column c receives the ranks' candidates in rank order
-            cnt_dev = allc_dev[:, :, 0].to(torch.int64)                            # [G, d]
-            mask = (torch.arange(maxc, device=self.device)[None, None, :] < cnt_dev[:, :, None]).permute(1, 0, 2)
-            mask = mask.reshape(d, G * maxc)
-            pos = torch.cumsum(mask, dim=1) - 1
-            dst = (torch.arange(d, device=self.device)[:, None] * cap + pos)[mask]
-            cval.reshape(-1)[dst] = gv.permute(1, 0, 2).reshape(d, G * maxc)[mask]
-            cmul.reshape(-1)[dst] = gm.permute(1, 0, 2).reshape(d, G * maxc)[mask]
-        sel[:, 4] = torch.as_tensor(totals.astype(np.int32)).to(self.device)
+        cval = bws[o2: o2 + 8 * d * cap].view(F64).reshape(d, cap)
+        cmul = bws[o3: o3 + 4 * d * cap].view(torch.int32).reshape(d, cap)
+        gsel = self.comm.allgather(sel[:, 4:6].contiguous())                      # [G, d, (count, overflow)]
+        gv = self.comm.allgather(cval[:, :capx].contiguous())                     # [G, d, capx]
+        gm = self.comm.allgather(cmul[:, :capx].contiguous())
+        _lib.check(lib.tb_bucket_merge(ptr(gsel), ptr(gv), ptr(gm), G, d, capx, ptr(bws), st), "tb_bucket_merge")
         stage(3, out, ovf)
         return int(ovf.item()) == 0
 
