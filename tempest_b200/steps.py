@@ -146,13 +146,33 @@ def numpy_lerp(a: float, b: float, t: float) -> float:
 # ======================================================================================
 # shared device helpers
 # ======================================================================================
+# Workspaces are pooled per process and device: a Sampler leases one and hands it back when it is garbage-collected, so the
+# next Sampler finds every named scratch buffer already allocated.  On a multi-GPU box a cudaMalloc has to map the new
+# block into every peer (5-10 ms each with peer access enabled): the four or five a fresh workspace needs in its first
+# trained iteration were a 30 ms spike at 8 GPUs.  Kernels never rely on workspace contents surviving between calls
+# (tickets / counters reset themselves, status words are cleared per call), so stale contents are harmless.
+_WS_POOL: dict = {}
+
+
+def _ws_acquire(device: torch.device) -> "Workspace":
+    idle = _WS_POOL.setdefault(device.index, [])
+    ws = idle.pop() if idle else Workspace(device)
+    ws.hint = 0
+    return ws
+
+
+def _ws_release(index, ws) -> None:
+    _WS_POOL.setdefault(index, []).append(ws)
+
+
 class Kernels:
     """Thin typed wrappers over the C ABI bound to one device / workspace."""
 
     def __init__(self, device: torch.device):
         self.device = device
         self.lib = _lib.load()
-        self.ws = Workspace(device)
+        self.ws = _ws_acquire(device)
+        weakref.finalize(self, _ws_release, device.index, self.ws)
         self._probe_ws = self.ws.bytes("probe", self.lib.tb_probe_workspace_bytes())
         self._reduce_ws = self.ws.bytes("reduce", self.lib.tb_reduce_workspace_bytes())
         self.probe_out = torch.zeros(16, dtype=F64, device=device)
