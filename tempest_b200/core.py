@@ -102,10 +102,10 @@ class SamplerCore:
             # (a second Comm / PeerCollectives / table memory); both streams issue the same call sequence on every rank
             from .dist import Comm as _Comm
 
-            self.k_side = ShardedKernels(self.device, _Comm())
+            self.k_side = ShardedKernels(self.device, _Comm(), role="side")
             self.k_side.defer_checks = True
         else:
-            self.k_side = Kernels(self.device) if self.overlap else None
+            self.k_side = Kernels(self.device, role="side") if self.overlap else None
         if self.comm.on:
             from .ensemble import PersistentEnsemble as _PE
 

@@ -96,15 +96,15 @@ class PeerCollectives:
 
 class ShardedKernels(Kernels):
     BUCKET_SLOTS = 1024      # candidate slots per column and rank gathered by the sharded bucket select
-    def __init__(self, device: torch.device, comm: Comm):
-        super().__init__(device)
+    def __init__(self, device: torch.device, comm: Comm, role: str = "main"):
+        super().__init__(device, role)
         import weakref
 
         self.comm = comm
         self.sharded = True
         self._leased = []                                   # (pool key, object) pairs, returned when this object dies
         weakref.finalize(self, _pool_release, self._leased)
-        self._pool_tag = (device.index, comm.world, id(comm.group) if comm.group is not None else 0)
+        self._pool_tag = (device.index, comm.world, id(comm.group) if comm.group is not None else 0, role)
         self.xgpu = self._setup_xgpu()
         if self.xgpu is not None and comm.fast is None:
             import os

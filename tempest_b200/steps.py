@@ -154,25 +154,27 @@ def numpy_lerp(a: float, b: float, t: float) -> float:
 _WS_POOL: dict = {}
 
 
-def _ws_acquire(device: torch.device) -> "Workspace":
-    idle = _WS_POOL.setdefault(device.index, [])
+def _ws_acquire(device: torch.device, role: str) -> "Workspace":
+    # keyed by role: the main-stream and the side-stream workspace of a Sampler hold different named buffers, and handing
+    # one out as the other would re-allocate everything while the pool still holds the blocks
+    idle = _WS_POOL.setdefault((device.index, role), [])
     ws = idle.pop() if idle else Workspace(device)
     ws.hint = 0
     return ws
 
 
-def _ws_release(index, ws) -> None:
-    _WS_POOL.setdefault(index, []).append(ws)
+def _ws_release(key, ws) -> None:
+    _WS_POOL.setdefault(key, []).append(ws)
 
 
 class Kernels:
     """Thin typed wrappers over the C ABI bound to one device / workspace."""
 
-    def __init__(self, device: torch.device):
+    def __init__(self, device: torch.device, role: str = "main"):
         self.device = device
         self.lib = _lib.load()
-        self.ws = _ws_acquire(device)
-        weakref.finalize(self, _ws_release, device.index, self.ws)
+        self.ws = _ws_acquire(device, role)
+        weakref.finalize(self, _ws_release, (device.index, role), self.ws)
         self._probe_ws = self.ws.bytes("probe", self.lib.tb_probe_workspace_bytes())
         self._reduce_ws = self.ws.bytes("reduce", self.lib.tb_reduce_workspace_bytes())
         self.probe_out = torch.zeros(16, dtype=F64, device=device)
