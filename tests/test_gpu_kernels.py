@@ -660,3 +660,55 @@ def test_guided_search_equals_plain_search(env):
         assert env.lib.tb_search_right_guided(env.ptr(cdf), n, env.ptr(du), m, env.ptr(guide), bits, env.ptr(out),
                                               env.sp()) == 0
         np.testing.assert_array_equal(out.cpu().numpy(), ref, err_msg=f"bits={bits}")
+
+
+def test_scale_inplace_dev_divides_by_device_scalar(env):
+    rng = np.random.default_rng(21)
+    w = rng.random(100003)
+    dw = dev_arr(env, w)
+    den = dev_arr(env, np.array([0.0, 3.7, 0.0]))
+    env._lib.check(env.lib.tb_scale_inplace_dev(env.ptr(dw), len(w), env.ptr(den[1:]), env.sp()))
+    assert np.array_equal(dw.cpu().numpy(), w / 3.7)
+
+
+def test_bucket_merge_concatenates_rank_lists_in_rank_order(env):
+    """Sharded order statistics: the all-gathered candidate lists of the ranks are merged on the device."""
+    G, d, capx, cap = 3, 2, 8, 65536
+    rng = np.random.default_rng(22)
+    counts = np.array([[3, 0], [8, 5], [1, 2]], dtype=np.int32)             # [G][d]
+    gsel = np.zeros((G, d, 2), dtype=np.int32)
+    gsel[:, :, 0] = counts
+    gval = rng.random((G, d, capx))
+    gmul = rng.integers(1, 9, size=(G, d, capx)).astype(np.int32)
+    off = np.zeros(4, dtype=np.int64)
+    env._lib.check(env.lib.tb_bucket_offsets(d, off.ctypes.data))
+    o0, o1, o2, o3 = [int(v) for v in off]
+    ws = torch.zeros(int(env.lib.tb_unit_median_workspace_bytes(d)), dtype=torch.uint8, device=env.dev)
+    a, b, c = dev_arr(env, gsel), dev_arr(env, gval), dev_arr(env, gmul)
+    env._lib.check(env.lib.tb_bucket_merge(env.ptr(a), env.ptr(b), env.ptr(c), G, d, capx, env.ptr(ws), env.sp()))
+    sel = ws[o1: o1 + 24 * d].view(torch.int32).reshape(d, 6).cpu().numpy()
+    cval = ws[o2: o2 + 8 * d * cap].view(torch.float64).reshape(d, cap).cpu().numpy()
+    cmul = ws[o3: o3 + 4 * d * cap].view(torch.int32).reshape(d, cap).cpu().numpy()
+    for col in range(d):
+        want_v = np.concatenate([gval[r, col, : counts[r, col]] for r in range(G)])
+        want_m = np.concatenate([gmul[r, col, : counts[r, col]] for r in range(G)])
+        assert sel[col, 4] == len(want_v) and sel[col, 5] == 0
+        np.testing.assert_array_equal(cval[col, : len(want_v)], want_v)
+        np.testing.assert_array_equal(cmul[col, : len(want_m)], want_m)
+    gsel[1, 0, 0] = capx + 1                                                 # a rank with more candidates than slots
+    a = dev_arr(env, gsel)
+    env._lib.check(env.lib.tb_bucket_merge(env.ptr(a), env.ptr(b), env.ptr(c), G, d, capx, env.ptr(ws), env.sp()))
+    sel = ws[o1: o1 + 24 * d].view(torch.int32).reshape(d, 6).cpu().numpy()
+    assert sel[0, 5] == 1 and sel[1, 5] == 0
+
+
+def test_xgpu_bench_grid_reduction_checksum(env):
+    """The in-kernel synchronisation point of the persistent kernels (grid_xreduce) on one GPU: every CTA must see the
+    sum over all CTAs at every one of `count` back-to-back synchronisation points."""
+    grid, count = 2 * int(env.lib.tb_sm_count()), 200
+    ws = torch.zeros(int(env.lib.tb_xgpu_bench_workspace_bytes(grid)) + 256, dtype=torch.uint8, device=env.dev)
+    out = torch.zeros(2, dtype=torch.float64, device=env.dev)
+    env._lib.check(env.lib.tb_xgpu_bench(None, grid, count, env.ptr(ws), env.ptr(out), env.sp()))
+    h = out.cpu().numpy()
+    assert h[1] == float(sum(k & 7 for k in range(count)) * grid)
+    assert 0.0 < h[0] < 1e6                                                  # ns per synchronisation point

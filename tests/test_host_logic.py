@@ -178,3 +178,25 @@ def test_plain_c_caller_compiles_and_links_against_the_abi(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     assert out.exists()
+
+
+def test_symmetric_pool_leases_and_returns_objects():
+    """sharded._pool_acquire / _pool_release: an idle object that fits is reused, otherwise the factory runs."""
+    from tempest_b200 import sharded
+
+    sharded._SYMM_POOL.pop(("t",), None)
+    made = []
+
+    def factory():
+        made.append(object())
+        return {"cap": 10 * len(made), "id": made[-1]}
+
+    a = sharded._pool_acquire(("t",), factory)
+    leased = [(("t",), a)]
+    sharded._pool_release(leased)
+    assert leased == [] and len(made) == 1
+    assert sharded._pool_acquire(("t",), factory, fits=lambda o: o["cap"] >= 5) is a          # reused
+    sharded._pool_release([(("t",), a)])
+    b = sharded._pool_acquire(("t",), factory, fits=lambda o: o["cap"] >= 15)                 # too small: a new one
+    assert b is not a and len(made) == 2
+    sharded._SYMM_POOL.pop(("t",), None)
