@@ -200,3 +200,31 @@ def test_symmetric_pool_leases_and_returns_objects():
     b = sharded._pool_acquire(("t",), factory, fits=lambda o: o["cap"] >= 15)                 # too small: a new one
     assert b is not a and len(made) == 2
     sharded._SYMM_POOL.pop(("t",), None)
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` runs the UNMODIFIED reference (oracle/_ref) on the host and prints ONE JSON line with
+    the contract keys; a non-zero rank exits without work.  Tiny N so it takes seconds."""
+    import json
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "tempest")):
+        pytest.skip("oracle/_ref not built here (python oracle/build_ref.py needs /root/reference)")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--ref-particles", "64"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["higher_is_better"] is True and j["unit"] == "PS iterations/s"
+    assert j["value"] > 0 and j["steps"] == 2 and j["warmup"] == 1
+    assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] == 1
+    assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
+    assert j["config"]["n_particles"] == 64 and "extrapolated_to_2pow20" in j
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=60, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
