@@ -117,7 +117,8 @@ uint64_t* tb_cdf_chain_diag_ptr(void* workspace, int64_t n);
  * Tile tables and the elements of the few tiles that cross a binade travel by peer stores between the
  * stages; every rank launches the same call.  cdf receives this rank's part of numpy's cumsum of the global
  * vector, bit for bit.  tb_cdf_status_ptr: device int32[16] {tiles, segments, runs, hard tiles, error code (0 ok,
- * 3 peer timeout, 4/5 table capacity, 6 refuted hypothesis), ...}; tb_cdf_total_ptr: device double cdf[-1]. */
+ * 3 peer timeout, 4/5 table capacity, 6 refuted hypothesis, 7 chained kernel: a predecessor tile never published), ...};
+ * tb_cdf_total_ptr: device double cdf[-1]. */
 typedef struct tb_cdf_x {
   int32_t rank, world;
   uint64_t seq;

@@ -1175,7 +1175,7 @@ __device__ __forceinline__ int chain_look_back(const ChainWs& w, long long g, in
 
 struct ChainShared {
   long long g;
-  unsigned long long hint;
+  unsigned long long t_start;                   // diagnostics: time at which this tile's start value became known
   long long F0[kChainWarps], F1[kChainWarps];   // per-warp totals under the candidate binades (Ec, Ec + 1); -1: none
   long long FE[kChainWarps];                    // per-warp totals under the binade of the tile's exact start value
   int zero[kChainWarps];                        // warp's part of the tile is all zeros (or empty)
@@ -1303,7 +1303,7 @@ cdf_chain_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ c
         const unsigned long long t_in = global_ns();
         atomicAdd(w.head->diag + 7, t_agg - t_ticket);
         atomicAdd(w.head->diag + 8, t_in - t_agg);
-        sm.hint = t_in;                 // (slot reused: start-of-emit time of this tile)
+        sm.t_start = t_in;
       }
     }
     // ---- 3. per-warp exact start values, the tile's end value first when it is plain, then the cdf values ------------
@@ -1365,7 +1365,7 @@ cdf_chain_kernel(const double* __restrict__ p, int64_t n, double* __restrict__ c
       hand_on(s_end);
       if (lane == 0) atomicAdd(w.head->diag + 5, 1ull);
     }
-    if (g > 0 && wid == kChainWarps - 1 && lane == 0) atomicAdd(w.head->diag + 9, global_ns() - sm.hint);
+    if (g > 0 && wid == kChainWarps - 1 && lane == 0) atomicAdd(w.head->diag + 9, global_ns() - sm.t_start);
   }
 }
 
