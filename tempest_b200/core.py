@@ -7,6 +7,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional, Union
 
@@ -92,8 +93,6 @@ class SamplerCore:
         # multinomial resampling): the cv diagnostic and the resampling overlap with the Trainer
         self.overlap = (config.volume_variation is None and not config.clustering and config.resample == "mult"
                         and (not self.comm.on or self.k.comm.fast is not None))
-        import os
-
         if os.environ.get("TEMPEST_B200_OVERLAP", "1") == "0":
             self.overlap = False
         self.side = torch.cuda.Stream(self.device) if self.overlap else None
@@ -113,6 +112,8 @@ class SamplerCore:
                 if kk is not None:
                     kk.prepare(self.n_local, config.n_dim, self.n_global * _PE.RESERVE_GENERATIONS)
         self._cv_pending = None
+        self._nvtx = os.environ.get("TEMPEST_B200_NVTX", "0") == "1"
+        self._nvtx_open = False
         self.reweighter = Reweighter(self)
         self.trainer = Trainer(self)
         self.resampler = Resampler(self)
@@ -278,7 +279,14 @@ class SamplerCore:
         return 1.0 - float(self.state.raw("beta")) >= 1e-4 or h[3] < self.n_total
 
     def _stage(self, name: str):
-        """CUDA-event stage timer (enabled by ``self.profile = True``; bench.py reads ``stage_ms``)."""
+        """CUDA-event stage timer (enabled by ``self.profile = True``; bench.py reads ``stage_ms``).  With
+        TEMPEST_B200_NVTX=1 every stage is also an NVTX range (readable nsys / ncu timelines), at no cost otherwise."""
+        if self._nvtx:
+            if self._nvtx_open:
+                torch.cuda.nvtx.range_pop()
+            self._nvtx_open = name != "end"
+            if self._nvtx_open:
+                torch.cuda.nvtx.range_push("ps:" + name)
         if not getattr(self, "profile", False):
             return
         ev = torch.cuda.Event(enable_timing=True)
